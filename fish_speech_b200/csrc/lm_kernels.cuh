@@ -1,0 +1,144 @@
+// Memory-bound kernels of the Dual-AR step that sit between the tensor-core GEMMs.  Each one is the
+// consumer of a GEMM's fp32 stream-K partials: it sums the partials in a fixed order, rounds to bf16
+// at exactly the points where the reference's bf16 tensors round (llama.py:990-1001 RMSNorm,
+// :891-908 qk-norm/RoPE, :979-987 SwiGLU, :842-845 residual adds) and produces the next GEMM's
+// operand.
+#pragma once
+#include "common.cuh"
+
+namespace fsb {
+
+// fp32 partials of one GEMM: value(row j, feature i) = sum_{s < nparts[i/128]} ws[s*slot_stride + j*ld + i]
+struct Partials {
+    const float* ws;
+    long long slot_stride;
+    int ld;
+    const int* nparts;  // per 128-feature tile; null => 1
+};
+
+struct EmbedArgs {
+    const int* tokens;  // [rows][C+1] (row-major per token row)
+    const __nv_bfloat16* emb;     // [V, D]
+    const __nv_bfloat16* cb_emb;  // [C*cs, D]
+    __nv_bfloat16* x;             // [rows, D]
+    int rows, D, C, cs, vocab;
+    int sem_begin, sem_end;
+    int scale;  // scale_codebook_embeddings
+};
+int launch_embed(const EmbedArgs& a, cudaStream_t st);
+
+// x_out = rbf(x_in + rbf(sum partials + bias))   (skip the add when parts.ws == null)
+// n_out = rbf(rbf(x_out * rsqrt(mean(x_out^2)+eps)) * w)     [fish RMSNorm: round, then * weight]
+struct ResidNormArgs {
+    Partials parts;
+    const __nv_bfloat16* bias;  // [D] or null (attention_o_bias)
+    const __nv_bfloat16* x_in;  // [rows, D] residual input (null => 0)
+    __nv_bfloat16* x_out;       // [rows, D] (may alias x_in; null => don't store)
+    const __nv_bfloat16* norm_w;  // [D] (null => no norm output)
+    __nv_bfloat16* n_out;         // [rows, D]
+    const int* gather;      // optional: output row r takes input row gather[map(r) * gather_stride]
+    const int* gather_map;  // optional row -> slot map applied before the gather lookup
+    int rows, D;
+    float eps;
+};
+int launch_resid_norm(const ResidNormArgs& a, cudaStream_t st);
+// gather[r * gather_stride] names the x_in row of output row r (embedding lookups)
+int launch_resid_norm_g(const ResidNormArgs& a, int gather_stride, cudaStream_t st);
+
+// y = rbf(sum partials + bias)  -> bf16 rows (fast_project_in)
+struct LinearOutArgs {
+    Partials parts;
+    const __nv_bfloat16* bias;
+    __nv_bfloat16* y;
+    int rows, N;
+};
+int launch_linear_out(const LinearOutArgs& a, cudaStream_t st);
+
+// q,k,v = rbf(partials [+bias]); optional per-head nn.RMSNorm (single rounding); interleaved RoPE in
+// fp32 with bf16 tables; q -> qbuf[row][H][Dh]; k,v -> cache[b][hkv][pos][Dh].
+struct QkvPrepArgs {
+    Partials parts;
+    const __nv_bfloat16* bias;  // [(H+2Hkv)*Dh] or null
+    const __nv_bfloat16* q_norm;  // [Dh] or null
+    const __nv_bfloat16* k_norm;
+    const __nv_bfloat16* freqs;  // [S, Dh/2, 2] bf16 (cos, sin)
+    const int* row_seq;          // [rows] cache slot of each row
+    const int* row_pos;          // [rows] position of each row
+    __nv_bfloat16* q;            // [rows, H, Dh]
+    __nv_bfloat16* kcache;       // [Bslots, Hkv, S, Dh]
+    __nv_bfloat16* vcache;
+    int rows, H, Hkv, Dh, S;
+    float eps;
+};
+int launch_qkv_prep(const QkvPrepArgs& a, cudaStream_t st);
+
+// out[row][h][:] = softmax(q.k^T * scale over cache positions [max(0,pos-window+1), pos]) . v
+// bf16_math = 1 reproduces the fast-AR hand-rolled attention (llama.py:948-976): scores, scaled
+// scores, probabilities and the output are each rounded to bf16.
+struct AttnArgs {
+    const __nv_bfloat16* q;  // [rows, H, Dh]
+    const __nv_bfloat16* kcache;
+    const __nv_bfloat16* vcache;
+    const int* row_seq;
+    const int* row_pos;
+    __nv_bfloat16* out;  // [rows, H*Dh]
+    int rows, H, Hkv, Dh, S;
+    int window;  // <=0: unlimited
+    int bf16_math;
+};
+int launch_attn(const AttnArgs& a, cudaStream_t st);
+
+// h = rbf( rbf(silu(rbf(a))) * rbf(c) ), a = feature i, c = feature I+i of the fused w1|w3 GEMM
+struct SwigluArgs {
+    Partials parts;
+    __nv_bfloat16* h;  // [rows, I]
+    int rows, I;
+};
+int launch_swiglu(const SwigluArgs& a, cudaStream_t st);
+
+struct SampleArgs {
+    Partials parts;  // logits of the (restricted) head: n entries per row
+    int n;           // number of candidate entries (<= 8192)
+    int rows;
+    // sampling parameters
+    float temperature, top_p;
+    int top_k;
+    // token mapping for the slow head: entry e -> token id (e < n_sem ? sem_begin + e : im_end_id)
+    int slow;  // 1: slow head (RAS + token mapping), 0: fast head (codes)
+    int n_sem, sem_begin, im_end_id, codebook_size;
+    int use_ras;              // RAS only in decode frames (previous_tokens given)
+    int* ras_window;          // [rows][10] ring of previous main tokens (slow only)
+    int ras_update;           // push the chosen token into the window
+    unsigned long long seed;  // Philox key
+    const unsigned long long* rng_offset;  // device counter (frame index) mixed into the stream
+    int draw_id;              // distinguishes the samples of one frame
+    // outputs
+    int* cur_tok;     // [rows][C+1]
+    int cb_index;     // slow: writes column 0 (token) and 1 (code a0); fast: writes column cb_index+1
+    int num_cb;
+    float* logits_out;  // optional [rows][n] fp32 copy of the bf16-rounded logits (tests)
+    int* finished;      // slow only: set when token == im_end
+    const int* row_slot;  // optional: state (cur_tok / window / finished / logits_out) index of a row
+};
+int launch_sample(const SampleArgs& a, cudaStream_t st);
+
+// bookkeeping at the end of a frame for each row's slot:
+//   out_tokens[slot][c][n_out[slot]] = cur_tok[slot][c]; n_out[slot]++;
+//   pos[slot] = set_pos_rows ? row_pos_src[set_pos_rows[row]] + 1 : pos[slot] + 1;   step++
+struct FrameEndArgs {
+    const int* cur_tok;
+    int* out_tokens;  // [slots][C+1][T_cap]
+    int* n_out;
+    int* pos;
+    const int* row_slot;      // optional
+    const int* set_pos_rows;  // optional (prefill): last token row of each sequence
+    const int* row_pos_src;
+    unsigned long long* step;
+    int rows, ncols, T_cap;
+};
+int launch_frame_end(const FrameEndArgs& a, cudaStream_t st);
+
+int launch_gather_rows(const __nv_bfloat16* src, const int* idx, __nv_bfloat16* dst, int rows, int D,
+                       cudaStream_t st);
+
+}  // namespace fsb
