@@ -11,6 +11,8 @@
 
 namespace fsb {
 
+int gemm_init();
+
 namespace {
 
 constexpr int kBlockM = 128;
@@ -367,8 +369,7 @@ template <int BN>
 int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        FSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FSB_TRY(gemm_init());
         attr_set = true;
     }
     gemm_tc_kernel<BN><<<plan.grid, kThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.p);
@@ -455,6 +456,16 @@ void gemm_plan_free(GemmPlan* plan) {
     plan->cta_items_dev = nullptr;
     plan->sched_dev = nullptr;
     plan->nparts_dev = nullptr;
+}
+
+int gemm_init() {
+    // opt every instantiation into the large dynamic shared-memory carve-out up front, so that no
+    // attribute call is needed later (e.g. while a stream is being captured into a CUDA graph)
+    FSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return 0;
 }
 
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {

@@ -82,5 +82,6 @@ int gemm_plan_init(GemmPlan* plan, const GemmOperand& A, const GemmOperand& B, i
 int gemm_plan_streamk(GemmPlan* plan, int tiles_i, int kblocks, int num_ctas);
 void gemm_plan_free(GemmPlan* plan);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+int gemm_init();  // set kernel attributes (idempotent)
 
 }  // namespace fsb

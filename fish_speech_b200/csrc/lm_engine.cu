@@ -369,6 +369,10 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     FSB_CHECK(prop.major == 10, "fishb200 kernels are built for sm_100a only (device is sm_%d%d)", prop.major,
               prop.minor);
     h->num_sms = prop.multiProcessorCount;
+    if (gemm_init() != 0 || attn_init() != 0) {
+        delete h;
+        return 1;
+    }
 
     auto B16 = [](const void* p) { return reinterpret_cast<const bf16*>(p); };
     h->emb = B16(w->d_embeddings);
@@ -440,7 +444,7 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     TRYC(dalloc(h, &h->n_out, cfg->max_batch, "n_out"));
     TRYC(dalloc(h, &h->pos, kDecRows, "pos"));
     TRYC(dalloc(h, &h->finished, cfg->max_batch, "finished"));
-    TRYC(dalloc(h, &h->ras_window, static_cast<size_t>(cfg->max_batch) * 10));
+    TRYC(dalloc(h, &h->ras_window, static_cast<size_t>(cfg->max_batch) * 10, "ras_window"));
     TRYC(dalloc(h, &h->iota, kDecRows));
     TRYC(dalloc(h, &h->fpos, static_cast<size_t>(C) * kDecRows));
     TRYC(dalloc(h, &h->step, 1));

@@ -511,15 +511,18 @@ static int launch_attn_t(const AttnArgs& a, cudaStream_t st) {
     const size_t smem = (static_cast<size_t>(G) * DH + static_cast<size_t>(G) * lcap +
                          static_cast<size_t>(kAttnWarps) * G * DH) * sizeof(float);
     FSB_CHECK(smem <= 200 * 1024, "attention: context %d too long for the shared-memory score buffer", lcap);
-    static size_t cur_attr = 0;
-    if (smem > 48 * 1024 && smem > cur_attr) {
-        FSB_CUDA(cudaFuncSetAttribute(attn_kernel<DH, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      200 * 1024));
-        cur_attr = 200 * 1024;
-    }
     const float scale = 1.0f / sqrtf(static_cast<float>(DH));
     attn_kernel<DH, G><<<dim3(a.Hkv, a.rows), kAttnThreads, smem, st>>>(a, scale, lcap);
     FSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int attn_init() {
+#define FSB_ATTN_ATTR(DH_, G_) \
+    FSB_CUDA(cudaFuncSetAttribute(attn_kernel<DH_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FSB_ATTN_ATTR(128, 1) FSB_ATTN_ATTR(128, 2) FSB_ATTN_ATTR(128, 4) FSB_ATTN_ATTR(128, 8)
+    FSB_ATTN_ATTR(64, 1) FSB_ATTN_ATTR(64, 2) FSB_ATTN_ATTR(64, 4) FSB_ATTN_ATTR(64, 8)
+#undef FSB_ATTN_ATTR
     return 0;
 }
 

@@ -87,6 +87,7 @@ struct AttnArgs {
     int bf16_math;
 };
 int launch_attn(const AttnArgs& a, cudaStream_t st);
+int attn_init();  // set kernel attributes (idempotent)
 
 // h = rbf( rbf(silu(rbf(a))) * rbf(c) ), a = feature i, c = feature I+i of the fused w1|w3 GEMM
 struct SwigluArgs {

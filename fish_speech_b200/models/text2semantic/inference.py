@@ -1,0 +1,524 @@
+"""Drop-in surface of fish_speech/models/text2semantic/inference.py.
+
+Same entry points and semantics (`init_model`, `decode_one_token_ar`, `decode_n_tokens`, `generate`,
+`generate_long`, `launch_thread_safe_queue`, `load_codec_model`, `encode_audio`, `decode_to_audio`, the
+click `main`), with the per-frame math executed by the CUDA engine.  New on top of the reference:
+`generate_batch` — up to 32 independent utterances decoded in lock-step on one GPU (the reference is
+batch-1 only: inference.py:87, 284-288).
+
+The CPU-side prompt builder (Conversation / ContentSequence / tokenizer) is the reference's own code
+(ADJACENT, unchanged) and is imported lazily from an installed `fish_speech`.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+import time
+import traceback
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Callable, Literal, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from .llama import IM_END_TOKEN, DualARTransformer
+
+try:  # loguru is what the reference logs with; fall back to stdlib logging if absent
+    from loguru import logger
+except Exception:  # pragma: no cover
+    import logging
+
+    logger = logging.getLogger("fish_speech_b200")
+
+RAS_WIN_SIZE = 10  # inference.py:49-51 (the engine implements the same constants)
+RAS_HIGH_TEMP = 1.0
+RAS_HIGH_TOP_P = 0.9
+_CHECK_EVERY = 8  # frames between host polls of the on-device finished flags
+
+
+def _as_float(v) -> float:
+    return float(v.item()) if isinstance(v, torch.Tensor) else float(v)
+
+
+def _ensure_engine(model: DualARTransformer, batch: int = 1):
+    if model.engine is None or model.max_batch_size < batch:
+        model.setup_caches(max_batch_size=max(batch, max(model.max_batch_size, 1)),
+                           max_seq_len=model.config.max_seq_len, dtype=model.dtype)
+        model._cache_setup_done = True
+    return model.engine
+
+
+def decode_one_token_ar(
+    model: DualARTransformer,
+    x: torch.Tensor,
+    input_pos: torch.Tensor,
+    temperature,
+    top_p,
+    top_k: int,
+    semantic_logit_bias: Optional[torch.Tensor] = None,
+    audio_masks: Optional[torch.Tensor] = None,
+    audio_parts: Optional[torch.Tensor] = None,
+    previous_tokens: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """One frame for one sequence (inference.py:96-181): x [1, C+1, S] at positions input_pos [S];
+    S > 1 is a prefill. Returns int tensor [C+1, 1].  `semantic_logit_bias` is accepted for signature
+    compatibility; the engine applies the same constraint by restricting the LM head to the selectable
+    rows (semantic ids + <|im_end|>)."""
+    if audio_parts is not None:
+        raise NotImplementedError("audio_parts: the reference model has no audio_projector either (llama.py:423-433)")
+    eng = _ensure_engine(model, 1)
+    seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+    sp = eng.sampling(_as_float(temperature), _as_float(top_p), int(top_k), seed)
+    C1 = model.config.num_codebooks + 1
+    x = x.view(1, C1, -1)
+    S = x.shape[-1]
+    if S > 1:
+        start = int(input_pos[0].item())
+        eng.prefill([x[0]], [0], sp, start_pos=[start], do_sample=True)
+    else:
+        eng.buffer("cur_tok")[0].copy_(x[0, :, 0].to(torch.int32))
+        eng.buffer("pos")[0:1].copy_(input_pos.to(torch.int32).view(1))
+        win = eng.buffer("ras_window")
+        if previous_tokens is not None:
+            win[0].copy_(previous_tokens[0].to(torch.int32))
+        else:
+            win[0].fill_(-1)  # no RAS without a window (inference.py:133)
+        eng.decode(1, 1, sp, use_graph=False)
+    return eng.buffer("cur_tok")[0].clone().view(C1, 1)
+
+
+def decode_n_tokens(
+    model: DualARTransformer,
+    cur_token: torch.Tensor,
+    input_pos: torch.Tensor,
+    num_new_tokens: int,
+    temperature,
+    top_p,
+    top_k: int,
+    semantic_logit_bias: Optional[torch.Tensor] = None,
+    audio_masks: Optional[torch.Tensor] = None,
+    audio_parts: Optional[torch.Tensor] = None,
+    decode_one_token=decode_one_token_ar,
+):
+    """inference.py:184-238 — up to num_new_tokens frames after `cur_token`, stopping after <|im_end|>.
+    The frame loop runs as CUDA-graph replays; the <|im_end|> test stays on the device and is polled
+    every few frames instead of synchronising every frame (inference.py:233)."""
+    eng = _ensure_engine(model, 1)
+    C1 = model.config.num_codebooks + 1
+    seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+    sp = eng.sampling(_as_float(temperature), _as_float(top_p), int(top_k), seed)
+    eng.buffer("cur_tok")[0].copy_(cur_token.view(C1, -1)[:, -1].to(torch.int32))
+    eng.buffer("pos")[0:1].copy_(input_pos.to(torch.int32).view(-1)[:1])
+    eng.buffer("n_out").zero_()
+    eng.buffer("finished").zero_()
+    eng.buffer("ras_window").zero_()
+    num_new_tokens = min(int(num_new_tokens), eng.max_frames)
+    n = _run_frames(eng, 1, num_new_tokens, sp, first_frame_from_prefill=False)[0]
+    return eng.buffer("out_tokens")[0, :, :n].clone()
+
+
+def _run_frames(eng, batch: int, max_frames: int, sp, first_frame_from_prefill: bool):
+    """Decode until every sequence has emitted <|im_end|> (checked from frame index 1 on, as the
+    reference's loop does) or max_frames frames exist. Returns the kept frame count per sequence."""
+    im_end = eng.im_end_id
+    done = 1 if first_frame_from_prefill else 0
+    while done < max_frames:
+        step = min(_CHECK_EVERY, max_frames - done)
+        eng.decode(batch, step, sp, use_graph=True)
+        done += step
+        if done < max_frames and bool(eng.buffer("finished")[:batch].all().item()):
+            # every sequence has produced <|im_end|>; make sure it was at index >= 1
+            toks = eng.buffer("out_tokens")[:batch, 0, :done]
+            if bool(((toks[:, 1:] == im_end).any(dim=1)).all().item()) or not first_frame_from_prefill:
+                break
+    toks = eng.buffer("out_tokens")[:batch, 0, :done].cpu()
+    counts = []
+    for b in range(batch):
+        row = toks[b]
+        start = 1 if first_frame_from_prefill else 0
+        hits = (row[start:] == im_end).nonzero()
+        counts.append(int(hits[0].item()) + start + 1 if len(hits) else done)
+    return counts
+
+
+@torch.no_grad()
+def generate(
+    *,
+    model: DualARTransformer,
+    prompt: torch.Tensor,
+    max_new_tokens: int,
+    audio_masks: Optional[torch.Tensor] = None,
+    audio_parts: Optional[torch.Tensor] = None,
+    decode_one_token=decode_one_token_ar,
+    num_samples: int = 1,
+    **sampling_kwargs,
+):
+    """inference.py:243-359 — prompt [C+1, T] -> [C+1, T+n]."""
+    return generate_batch(model=model, prompts=[prompt], max_new_tokens=max_new_tokens,
+                          audio_masks=audio_masks, audio_parts=audio_parts, **sampling_kwargs)[0]
+
+
+@torch.no_grad()
+def generate_batch(
+    *,
+    model: DualARTransformer,
+    prompts: Sequence[torch.Tensor],
+    max_new_tokens: int,
+    audio_masks: Optional[torch.Tensor] = None,
+    audio_parts: Optional[torch.Tensor] = None,
+    **sampling_kwargs,
+) -> list[torch.Tensor]:
+    """`generate` for up to 32 independent utterances at once (one KV slot each). Every sequence sees
+    exactly the computation it would see alone: the kernels are batch-invariant, so the result for a
+    prompt does not depend on its batch neighbours."""
+    if audio_parts is not None:
+        raise NotImplementedError("audio_parts is not supported (nor by the reference model, llama.py:423-433)")
+    cfg = model.config
+    B = len(prompts)
+    if B < 1 or B > 32:
+        raise ValueError("generate_batch handles 1..32 prompts per call")
+    T_max = max(int(p.size(1)) for p in prompts)
+    for p in prompts:
+        if p.size(1) >= cfg.max_seq_len:
+            raise ValueError(f"Input sequence length {p.size(1)} exceeds max_seq_len {cfg.max_seq_len}")
+    if max_new_tokens:
+        if T_max + max_new_tokens > cfg.max_seq_len:
+            max_new_tokens = cfg.max_seq_len - T_max
+    else:
+        max_new_tokens = cfg.max_seq_len - T_max
+    eng = _ensure_engine(model, B)
+    max_new_tokens = min(max_new_tokens, eng.max_frames)
+    seed = int(sampling_kwargs.get("seed", torch.initial_seed())) & 0x7FFFFFFFFFFFFFFF
+    sp = eng.sampling(sampling_kwargs.get("temperature", 1.0), sampling_kwargs.get("top_p", 0.9),
+                      int(sampling_kwargs.get("top_k", 30)), seed)
+    eng.reset()
+    eng.prefill(list(prompts), list(range(B)), sp, do_sample=True)
+    counts = _run_frames(eng, B, max_new_tokens, sp, first_frame_from_prefill=True)
+    out_tokens = eng.buffer("out_tokens")
+    outs = []
+    for b, p in enumerate(prompts):
+        gen = out_tokens[b, :, : counts[b]].to(p.dtype)
+        outs.append(torch.cat([p.to(gen.device), gen], dim=1))
+    return outs
+
+
+def init_model(checkpoint_path, device, precision, compile=False):
+    """inference.py:362-392. `compile` is accepted and ignored: the frame is already one CUDA graph of
+    hand-written kernels, there is nothing for Inductor to do."""
+    if precision not in (torch.bfloat16, None):
+        logger.warning(f"fish_speech_b200 computes in bf16; requested {precision} is ignored")
+    model = DualARTransformer.from_pretrained(checkpoint_path, load_weights=True, device=device)
+    logger.info("Restored model from checkpoint")
+    logger.info("Using DualARTransformer (fish_speech_b200 CUDA engine)")
+    model.fixed_temperature = torch.tensor(0.7, device=device, dtype=torch.float)
+    model.fixed_top_p = torch.tensor(0.7, device=device, dtype=torch.float)
+    model.fixed_repetition_penalty = torch.tensor(1.5, device=device, dtype=torch.float)
+    model._cache_setup_done = False
+    return model.eval(), decode_one_token_ar
+
+
+# ---- codec helpers (inference.py:396-444) -------------------------------------------------------
+@torch.inference_mode()
+def load_codec_model(codec_checkpoint_path, device, precision=torch.bfloat16):
+    from ..dac.inference import load_model
+
+    return load_model("modded_dac_vq", codec_checkpoint_path, device=device)
+
+
+@torch.inference_mode()
+def encode_audio(audio_path, codec, device):
+    import torchaudio
+
+    wav, sr = torchaudio.load(str(audio_path))
+    if wav.shape[0] > 1:
+        wav = wav.mean(dim=0, keepdim=True)
+    wav = torchaudio.functional.resample(wav.to(device), sr, codec.sample_rate)[0]
+    audios = wav[None, None]
+    audio_lengths = torch.tensor([len(wav)], device=device, dtype=torch.long)
+    indices, feature_lengths = codec.encode(audios, audio_lengths)
+    return indices[0, :, : feature_lengths[0]]
+
+
+@torch.inference_mode()
+def decode_to_audio(codes, codec):
+    audio = codec.from_indices(codes[None])
+    return audio[0, 0]
+
+
+@dataclass
+class GenerateResponse:
+    action: Literal["sample", "next"]
+    codes: Optional[torch.Tensor] = None
+    text: Optional[str] = None
+
+
+def _reference_frontend():
+    """The reference's CPU prompt builder (content_sequence.py / conversation.py) — unchanged code."""
+    try:
+        from fish_speech.content_sequence import TextPart, VQPart
+        from fish_speech.conversation import Conversation, Message
+    except Exception as e:  # pragma: no cover
+        raise ImportError(
+            "generate_long needs the reference's CPU-side prompt builder (fish_speech.conversation / "
+            "content_sequence / tokenizer); install fish-speech next to fish_speech_b200") from e
+    return TextPart, VQPart, Conversation, Message
+
+
+def split_text_by_speaker(text: str) -> list[str]:
+    """inference.py:454-474."""
+    import re
+
+    pattern = r"(<\|speaker:\d+\|>)"
+    parts = re.split(pattern, text)
+    turns, i = [], 0
+    while i < len(parts):
+        part = parts[i].strip()
+        if re.match(pattern, part):
+            if i + 1 < len(parts):
+                turn = part + parts[i + 1]
+                turns.append(turn.strip())
+                i += 2
+            else:
+                turns.append(part)
+                i += 1
+        else:
+            i += 1
+    return turns
+
+
+def group_turns_into_batches(turns: list[str], max_speakers: int = 3, max_bytes: int = 300) -> list[str]:
+    """inference.py:477-520: close the current batch when it already holds `max_speakers` turns or the
+    next turn would push it over `max_bytes` UTF-8 bytes."""
+    batches: list[str] = []
+    held: list[str] = []
+    held_bytes = 0
+    for turn in turns:
+        size = len(turn.encode("utf-8"))
+        if len(held) >= max_speakers or (held and held_bytes + size > max_bytes):
+            batches.append("\n".join(held))
+            held, held_bytes = [], 0
+        held.append(turn)
+        held_bytes += size
+    if held:
+        batches.append("\n".join(held))
+    return batches
+
+
+def generate_long(
+    *,
+    model,
+    device: Union[str, torch.device],
+    decode_one_token: Callable,
+    text: str,
+    num_samples: int = 1,
+    max_new_tokens: int = 0,
+    top_p: float = 0.9,
+    top_k: int = 30,
+    repetition_penalty: float = 1.1,
+    temperature: float = 1.0,
+    compile: bool = False,
+    iterative_prompt: bool = True,
+    chunk_length: int = 512,
+    prompt_text: Optional[Union[str, list[str]]] = None,
+    prompt_tokens: Optional[Union[torch.Tensor, list[torch.Tensor]]] = None,
+):
+    """inference.py:523-733: build the conversation, generate chunk by chunk, yield codes per chunk."""
+    assert 0 < top_p <= 1, "top_p must be in (0, 1]"
+    assert 0 < temperature < 2, "temperature must be in (0, 2)"
+    TextPart, VQPart, Conversation, Message = _reference_frontend()
+
+    use_prompt = bool(prompt_text) and bool(prompt_tokens)
+    if use_prompt and isinstance(prompt_text, str):
+        prompt_text = [prompt_text]
+        prompt_tokens = [prompt_tokens]
+    if use_prompt:
+        assert len(prompt_text) == len(prompt_tokens), "Prompt text and tokens must have the same length"
+    if prompt_tokens:
+        prompt_tokens = [i.cpu() for i in prompt_tokens]
+
+    tokenizer = model.tokenizer
+    max_length = model.config.max_seq_len
+    base_conversation = Conversation()
+    if use_prompt:
+        tagged = []
+        for i, t in enumerate(prompt_text):
+            import re
+
+            tagged.append(t if re.search(r"<\|speaker:\d+\|>", t) else f"<|speaker:{i}|>{t}")
+        system_parts = [TextPart(text="convert the provided text to speech reference to the following:\n\nText:\n",
+                                 cal_loss=False)]
+        system_parts.append(TextPart(text="\n".join(tagged), cal_loss=False))
+        system_parts.append(TextPart(text="\n\nSpeech:\n", cal_loss=False))
+        all_codes = torch.cat([c for c in prompt_tokens], dim=1)
+        system_parts.append(VQPart(codes=all_codes, cal_loss=False))
+    else:
+        system_parts = [TextPart(text="convert the provided text to speech", cal_loss=False)]
+    base_conversation.append(Message(role="system", parts=system_parts, cal_loss=False, add_im_start=True,
+                                     add_im_end=True))
+
+    turns = split_text_by_speaker(text)
+    if turns:
+        batches = group_turns_into_batches(turns, max_speakers=5, max_bytes=chunk_length)
+    else:
+        batches = [text]
+    logger.info(f"Split into {len(turns)} turns, grouped into {len(batches)} batches")
+
+    for sample_idx in range(num_samples):
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        conversation = __import__("copy").deepcopy(base_conversation)
+        for batch_idx, batch_text in enumerate(batches):
+            logger.info(f"--- Sample {sample_idx}, Batch {batch_idx} ({len(batch_text.encode('utf-8'))} bytes) ---")
+            conversation.append(Message(role="user", parts=[TextPart(text=batch_text, cal_loss=False)],
+                                        cal_loss=False, add_im_start=True, add_im_end=True))
+            conversation_gen = __import__("copy").deepcopy(conversation)
+            conversation_gen.append(Message(role="assistant", parts=[], cal_loss=False, modality="voice",
+                                            add_im_start=True, add_im_end=False))
+            encoded, audio_masks, audio_parts = conversation_gen.encode_for_inference(
+                tokenizer, num_codebooks=model.config.num_codebooks)
+            logger.info(f"Encoded prompt shape: {encoded.shape}")
+            if encoded.size(1) > max_length - 2048:
+                raise ValueError(f"Prompt is too long: {encoded.size(1)} > {max_length - 2048}")
+            encoded = encoded.to(device=device)
+            prompt_length = encoded.size(1)
+            t0 = time.perf_counter()
+            y = generate(model=model, prompt=encoded, max_new_tokens=max_new_tokens, audio_masks=audio_masks,
+                         audio_parts=audio_parts, decode_one_token=decode_one_token, temperature=temperature,
+                         top_p=top_p, top_k=top_k)
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            t_batch = time.perf_counter() - t0
+            tokens_generated = y.size(1) - prompt_length
+            tokens_sec = tokens_generated / t_batch if t_batch > 0 else 0
+            logger.info(f"Batch {batch_idx}: Generated {tokens_generated} tokens in {t_batch:.02f} seconds, "
+                        f"{tokens_sec:.02f} tokens/sec")
+            codes = y[1:, prompt_length:-1].clone()
+            assert (codes >= 0).all(), f"Negative code found: {codes}"
+            conversation.append(Message(role="assistant", parts=[VQPart(codes=codes.cpu(), cal_loss=False)],
+                                        cal_loss=False, modality="voice", add_im_start=True, add_im_end=True))
+            yield GenerateResponse(action="sample", codes=codes, text=batch_text)
+            del y, encoded
+        if torch.cuda.is_available():
+            logger.info(f"GPU Memory used: {torch.cuda.max_memory_reserved() / 1e9:.02f} GB")
+        yield GenerateResponse(action="next")
+
+
+@dataclass
+class WrappedGenerateResponse:
+    status: Literal["success", "error"]
+    response: Optional[Union[GenerateResponse, Exception]] = None
+
+
+@dataclass
+class GenerateRequest:
+    request: dict
+    response_queue: queue.Queue
+
+
+def launch_thread_safe_queue(checkpoint_path, device, precision, compile: bool = False):
+    """inference.py:736-799: the model lives in ONE daemon worker thread fed by a queue; `None` shuts
+    it down; errors are returned as WrappedGenerateResponse(status="error", response=exc)."""
+    input_queue = queue.Queue()
+    init_event = threading.Event()
+
+    def worker():
+        model, decode_one_token = init_model(checkpoint_path, device, precision, compile=compile)
+        with torch.cuda.device(device):
+            model.setup_caches(max_batch_size=1, max_seq_len=model.config.max_seq_len, dtype=model.dtype)
+        init_event.set()
+        while True:
+            item: Optional[GenerateRequest] = input_queue.get()
+            if item is None:
+                break
+            kwargs = item.request
+            response_queue = item.response_queue
+            try:
+                for chunk in generate_long(model=model, decode_one_token=decode_one_token, **kwargs):
+                    response_queue.put(WrappedGenerateResponse(status="success", response=chunk))
+            except Exception as e:
+                logger.error(traceback.format_exc())
+                response_queue.put(WrappedGenerateResponse(status="error", response=e))
+
+    threading.Thread(target=worker, daemon=True).start()
+    init_event.wait()
+    return input_queue
+
+
+def main(argv=None):
+    """CLI with the reference's options (inference.py:802-838)."""
+    import click
+
+    @click.command()
+    @click.option("--text", type=str, default="<|speaker:0|>你说的对, 但是原神是一款由米哈游自主研发的开放世界手游.")
+    @click.option("--prompt-text", type=str, default=None, multiple=True)
+    @click.option("--prompt-tokens", type=click.Path(path_type=Path, exists=True), default=None, multiple=True)
+    @click.option("--prompt-audio", type=click.Path(path_type=Path, exists=True), default=None, multiple=True)
+    @click.option("--output", type=click.Path(path_type=Path), default=None)
+    @click.option("--num-samples", type=int, default=1)
+    @click.option("--max-new-tokens", type=int, default=0)
+    @click.option("--top-p", type=float, default=0.9)
+    @click.option("--top-k", type=int, default=30)
+    @click.option("--temperature", type=float, default=1.0)
+    @click.option("--checkpoint-path", type=click.Path(path_type=Path, exists=True), default="checkpoints/s2-pro")
+    @click.option("--device", type=str, default="cuda")
+    @click.option("--compile/--no-compile", default=False)
+    @click.option("--seed", type=int, default=42)
+    @click.option("--half/--no-half", default=False)
+    @click.option("--iterative-prompt/--no-iterative-prompt", default=True)
+    @click.option("--chunk-length", type=int, default=300)
+    @click.option("--output-dir", type=Path, default="output")
+    def _main(text, prompt_text, prompt_tokens, prompt_audio, output, num_samples, max_new_tokens, top_p, top_k,
+              temperature, checkpoint_path, device, compile, seed, half, iterative_prompt, chunk_length, output_dir):
+        os_makedirs = __import__("os").makedirs
+        os_makedirs(output_dir, exist_ok=True)
+        precision = torch.bfloat16
+        if prompt_text and not prompt_audio and not prompt_tokens:
+            raise ValueError("--prompt-text requires either --prompt-audio or --prompt-tokens")
+        if prompt_text and prompt_tokens and len(prompt_text) != len(prompt_tokens):
+            raise ValueError("Number of prompt text and prompt tokens should be the same")
+        model, decode_one_token = init_model(checkpoint_path, device, precision, compile=compile)
+        with torch.cuda.device(device):
+            model.setup_caches(max_batch_size=1, max_seq_len=model.config.max_seq_len, dtype=model.dtype)
+        codec = None
+        codec_path = Path(checkpoint_path) / "codec.pth"
+        prompt_tokens_list = None
+        if prompt_audio:
+            codec = load_codec_model(codec_path, device, precision)
+            prompt_tokens_list = [encode_audio(p, codec, device).cpu() for p in prompt_audio]
+        elif prompt_tokens:
+            prompt_tokens_list = [torch.from_numpy(np.load(p)) for p in prompt_tokens]
+        torch.manual_seed(seed)
+        if torch.cuda.is_available():
+            torch.cuda.manual_seed(seed)
+        generator = generate_long(model=model, device=device, decode_one_token=decode_one_token, text=text,
+                                  num_samples=num_samples, max_new_tokens=max_new_tokens, top_p=top_p, top_k=top_k,
+                                  temperature=temperature, compile=compile, iterative_prompt=iterative_prompt,
+                                  chunk_length=chunk_length, prompt_text=list(prompt_text) if prompt_text else None,
+                                  prompt_tokens=prompt_tokens_list)
+        idx, codes = 0, []
+        for response in generator:
+            if response.action == "sample":
+                codes.append(response.codes)
+            elif response.action == "next":
+                if codes:
+                    merged = torch.cat(codes, dim=1)
+                    np.save(Path(output_dir) / f"codes_{idx}.npy", merged.cpu().numpy())
+                    if output:
+                        if codec is None:
+                            codec = load_codec_model(codec_path, device, precision)
+                        audio = decode_to_audio(merged.to(device), codec)
+                        import soundfile as sf
+
+                        out = Path(output)
+                        if num_samples > 1:
+                            out = out.with_stem(f"{out.stem}_{idx}")
+                        sf.write(str(out), audio.float().cpu().numpy(), codec.sample_rate)
+                codes = []
+                idx += 1
+
+    return _main(argv, standalone_mode=False) if argv is not None else _main()
+
+
+if __name__ == "__main__":
+    main()

@@ -124,7 +124,7 @@ int fsb_lm_reset(fsb_lm* h, void* stream);
 
 /* Named device buffers of the handle, for reading results and for tests:
  *   "out_tokens" int32 [max_batch][C+1][max_frames], "n_out" int32 [max_batch], "pos" int32 [max_batch],
- *   "finished" int32 [max_batch], "cur_tok" int32 [max_batch][C+1],
+ *   "finished" int32 [max_batch], "cur_tok" int32 [max_batch][C+1], "ras_window" int32 [max_batch][10],
  *   debug only: "slow_logits" f32 [max_batch][head_rows], "fast_logits" f32 [C][max_batch][codebook_size],
  *   "hidden" bf16 [32][dim], "dbg_x" bf16 [n_layer+1][32][dim] */
 int fsb_lm_buffer(fsb_lm* h, const char* name, void** d_ptr, size_t* bytes);

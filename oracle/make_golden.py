@@ -1,0 +1,91 @@
+"""Pin the oracle against the REAL reference and write the golden fixtures (test infrastructure).
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden
+
+For every case it (1) runs the unmodified reference (imported through oracle/ref_stubs.py), (2) runs the
+oracle restatement on the same seeded weights / inputs, (3) asserts bit-equality, (4) stores inputs,
+seeds and the reference's outputs under tests/golden/.  The committed fixtures let the CPU test-suite
+and the GPU box (where /root/reference does not exist) re-check both the oracle and the CUDA path
+against outputs of the reference itself.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import lm_oracle as O  # noqa: E402
+from oracle import ref_stubs as R  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+
+# (name, config overrides, weight seed, head_gain, prompt len, new frames, top_k, temperature, top_p)
+LM_CASES = [
+    ("lm_tiny_greedy", {}, 11, 8.0, 12, 12, 1, 0.7, 0.7),
+    ("lm_tiny_topk", {}, 12, 1.0, 9, 10, 30, 0.7, 0.8),
+    ("lm_tiny_proj", dict(fast_dim=128, fast_n_head=2, fast_n_local_heads=1, fast_head_dim=64, fast_intermediate_size=256, attention_qk_norm=False,
+                          fast_attention_qk_norm=True, norm_fastlayer_input=False,
+                          scale_codebook_embeddings=False), 13, 8.0, 10, 8, 1, 0.7, 0.7),
+    ("lm_tiny_bias", dict(attention_qkv_bias=True, attention_o_bias=True, fast_attention_qkv_bias=True,
+                          fast_attention_o_bias=True, n_local_heads=2, fast_n_local_heads=4), 14, 8.0, 16, 8, 1, 0.7, 0.7),
+]
+
+
+def make_prompt(cfg: O.LMConfig, seed: int, T: int) -> torch.Tensor:
+    """Text ids with a short span of semantic tokens + codes in the middle (a voice-clone-like prompt)."""
+    g = torch.Generator().manual_seed(seed)
+    prompt = torch.zeros(cfg.num_codebooks + 1, T, dtype=torch.long)
+    prompt[0] = torch.randint(0, cfg.im_end_id, (T,), generator=g)
+    a, b = T // 3, min(T - 1, T // 3 + 3)
+    prompt[0, a:b] = cfg.semantic_begin_id + torch.randint(0, cfg.codebook_size, (b - a,), generator=g)
+    prompt[1:, a:b] = torch.randint(0, cfg.codebook_size, (cfg.num_codebooks, b - a), generator=g)
+    return prompt
+
+
+def run_lm_case(name, over, seed, head_gain, T, n, top_k, temp, top_p):
+    R.install()
+    from fish_speech.models.text2semantic import inference as ref_inf
+
+    cfg = O.tiny_config(**over)
+    w = O.make_weights(cfg, seed=seed, head_gain=head_gain)
+    model = R.reference_lm(cfg, w)
+    prompt = make_prompt(cfg, seed, T)
+    torch.manual_seed(seed)
+    ref = ref_inf.generate(model=model, prompt=prompt, max_new_tokens=n, audio_masks=None, audio_parts=None,
+                           temperature=temp, top_p=top_p, top_k=top_k).to(torch.int32)
+    st = O.setup(cfg, w)
+    traces = []
+    torch.manual_seed(seed)
+    got = O.generate(st, prompt, n, temperature=temp, top_p=top_p, top_k=top_k, traces=traces)
+    assert torch.equal(ref, got), f"{name}: oracle differs from the reference"
+    np.savez_compressed(
+        GOLD / f"{name}.npz",
+        config=np.array(repr(over)), weight_seed=seed, head_gain=head_gain, prompt=prompt.numpy(),
+        new_frames=n, top_k=top_k, temperature=temp, top_p=top_p, rng_seed=seed,
+        ref_tokens=ref.numpy(),
+        ref_slow_logits=torch.stack([t["slow_logits"] for t in traces]).numpy().astype(np.float32),
+    )
+    print(f"{name}: reference == oracle, {ref.shape[1] - T} frames -> {GOLD / (name + '.npz')}")
+
+
+def main():
+    GOLD.mkdir(parents=True, exist_ok=True)
+    for case in LM_CASES:
+        run_lm_case(*case)
+    try:
+        from oracle import make_golden_codec
+
+        make_golden_codec.main()
+    except ImportError:
+        print("codec goldens: oracle.make_golden_codec not present yet")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,68 @@
+"""Shared helpers for the LM parity tests (oracle config -> product model)."""
+from __future__ import annotations
+
+import ast
+
+import numpy as np
+import torch
+
+from oracle import lm_oracle as O
+
+
+def model_args(cfg: O.LMConfig):
+    from fish_speech_b200.models.text2semantic.llama import DualARModelArgs
+
+    return DualARModelArgs(
+        model_type="dual_ar", vocab_size=cfg.vocab_size, n_layer=cfg.n_layer, n_head=cfg.n_head, dim=cfg.dim,
+        intermediate_size=cfg.intermediate_size, n_local_heads=cfg.n_local_heads, head_dim=cfg.head_dim,
+        rope_base=cfg.rope_base, norm_eps=cfg.norm_eps, max_seq_len=cfg.max_seq_len,
+        tie_word_embeddings=cfg.tie_word_embeddings, attention_qkv_bias=cfg.attention_qkv_bias,
+        attention_o_bias=cfg.attention_o_bias, attention_qk_norm=cfg.attention_qk_norm,
+        codebook_size=cfg.codebook_size, num_codebooks=cfg.num_codebooks,
+        semantic_begin_id=cfg.semantic_begin_id, semantic_end_id=cfg.semantic_end_id,
+        scale_codebook_embeddings=cfg.scale_codebook_embeddings, n_fast_layer=cfg.n_fast_layer,
+        fast_dim=cfg.fast_dim, fast_n_head=cfg.fast_n_head, fast_n_local_heads=cfg.fast_n_local_heads,
+        fast_head_dim=cfg.fast_head_dim, fast_intermediate_size=cfg.fast_intermediate_size,
+        fast_attention_qkv_bias=cfg.fast_attention_qkv_bias, fast_attention_qk_norm=cfg.fast_attention_qk_norm,
+        fast_attention_o_bias=cfg.fast_attention_o_bias, norm_fastlayer_input=cfg.norm_fastlayer_input,
+    )
+
+
+def split_w13(weights: dict) -> dict:
+    """The product loads checkpoints in the reference's key naming (w1/w3 separate) — already the case."""
+    return weights
+
+
+def build_model(cfg: O.LMConfig, weights: dict, max_batch=1, debug=True, max_rows=2048):
+    from fish_speech_b200.models.text2semantic.llama import DualARTransformer
+
+    m = DualARTransformer(model_args(cfg), weights, device="cuda", im_end_id=cfg.im_end_id)
+    m.debug = debug
+    m.max_rows = max_rows
+    m.setup_caches(max_batch_size=max_batch, max_seq_len=cfg.max_seq_len)
+    m._cache_setup_done = True
+    return m
+
+
+def make_prompt(cfg: O.LMConfig, seed: int, T: int) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    prompt = torch.zeros(cfg.num_codebooks + 1, T, dtype=torch.long)
+    prompt[0] = torch.randint(0, cfg.im_end_id, (T,), generator=g)
+    a, b = T // 3, min(T - 1, T // 3 + 3)
+    prompt[0, a:b] = cfg.semantic_begin_id + torch.randint(0, cfg.codebook_size, (b - a,), generator=g)
+    prompt[1:, a:b] = torch.randint(0, cfg.codebook_size, (cfg.num_codebooks, b - a), generator=g)
+    return prompt
+
+
+def load_golden(path):
+    z = np.load(path, allow_pickle=False)
+    over = ast.literal_eval(str(z["config"]))
+    cfg = O.tiny_config(**over)
+    w = O.make_weights(cfg, seed=int(z["weight_seed"]), head_gain=float(z["head_gain"]))
+    return cfg, w, z
+
+
+def restricted(cfg: O.LMConfig, full_logits: torch.Tensor) -> torch.Tensor:
+    """Selectable rows of a full-vocabulary logit vector: semantic ids, then <|im_end|>."""
+    return torch.cat([full_logits[..., cfg.semantic_begin_id: cfg.semantic_end_id + 1],
+                      full_logits[..., cfg.im_end_id: cfg.im_end_id + 1]], dim=-1)

@@ -1,0 +1,166 @@
+"""Dual-AR engine (CUDA, through the C-ABI) against the oracle and against the committed outputs of
+the real reference.
+
+Tolerances: integer results (token ids / codebook indices) must be IDENTICAL wherever the oracle's
+decision is not a near-tie; logits are bf16 values of fp32 sums accumulated in a different order than
+the CPU's, so they are compared with atol = 2 bf16 ulps of the largest logit + 3% of the logit std.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lm_oracle as O
+from tests.lm_util import build_model, load_golden, make_prompt, restricted
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def _logit_tol(ref: torch.Tensor) -> float:
+    return float(ref.abs().max()) * 2 ** -7 + 0.03 * float(ref.std())
+
+
+def _gen(model, prompt, n, **kw):
+    from fish_speech_b200.models.text2semantic.inference import generate
+
+    return generate(model=model, prompt=prompt.cuda(), max_new_tokens=n, **kw).cpu()
+
+
+@pytest.mark.parametrize("name", sorted(p.name for p in GOLD.glob("lm_*.npz") if "topk" not in p.name))
+def test_greedy_tokens_match_reference_golden(name):
+    """Free-running greedy decode: every token id and codebook index equals the reference's."""
+    cfg, w, z = load_golden(GOLD / name)
+    model = build_model(cfg, w)
+    got = _gen(model, torch.from_numpy(z["prompt"]), int(z["new_frames"]), temperature=float(z["temperature"]),
+               top_p=float(z["top_p"]), top_k=int(z["top_k"]))
+    ref = torch.from_numpy(z["ref_tokens"])
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert torch.equal(got.to(torch.int32), ref), f"first mismatch at {(got != ref).nonzero()[:4].tolist()}"
+
+
+def test_prefill_and_decode_logits_teacher_forced():
+    """Per-frame slow/fast logits vs the oracle with the oracle's own tokens fed back (teacher forcing)."""
+    from fish_speech_b200.models.text2semantic.inference import decode_one_token_ar
+
+    cfg = O.tiny_config()
+    w = O.make_weights(cfg, seed=21, head_gain=4.0)
+    st = O.setup(cfg, w)
+    T, n = 11, 6
+    prompt = make_prompt(cfg, 21, T)
+    traces = []
+    ref = O.generate(st, prompt, n, temperature=0.7, top_p=0.7, top_k=1, traces=traces, stop_on_im_end=False)
+    model = build_model(cfg, w)
+    eng = model.engine
+    temp, top_p = torch.tensor(0.7), torch.tensor(0.7)
+    C1 = cfg.num_codebooks + 1
+    prev = torch.zeros((C1, 10), dtype=torch.int32)
+    for f in range(n):
+        if f == 0:
+            x, pos, pt = prompt.view(1, C1, -1).cuda(), torch.arange(T).cuda(), None
+        else:
+            x = ref[:, T + f - 1].view(1, C1, 1).cuda()  # the ORACLE's previous frame
+            pos, pt = torch.tensor([T + f - 1]).cuda(), prev.cuda()
+        tok = decode_one_token_ar(model, x, pos, temp, top_p, 1, None, None, None, previous_tokens=pt).cpu()
+        slow = eng.buffer("slow_logits")[0].cpu()
+        want = restricted(cfg, traces[f]["slow_logits"])
+        tol = _logit_tol(want)
+        assert (slow - want).abs().max().item() <= tol, f"frame {f}: slow logits off by {(slow - want).abs().max().item()} > {tol}"
+        fast = eng.buffer("fast_logits")[: cfg.num_codebooks - 1, 0].cpu()
+        # fast logits depend on the sampled codes: compare only while our codes equal the oracle's
+        same = torch.equal(tok.view(-1).to(torch.int32), ref[:, T + f].to(torch.int32))
+        assert same, f"frame {f}: tokens {tok.view(-1).tolist()} vs oracle {ref[:, T + f].tolist()}"
+        for p in range(cfg.num_codebooks - 1):
+            wantf = traces[f]["fast_logits"][p]
+            assert (fast[p] - wantf).abs().max().item() <= _logit_tol(wantf), f"frame {f} fast pass {p + 1}"
+        if f > 0:
+            prev = prev.roll(-1, dims=1)
+            prev[:, -1] = ref[:, T + f].to(torch.int32)
+
+
+def test_batch_invariance_and_ragged_prompts():
+    """Batch-32-style decode: each sequence of a ragged batch equals its solo run and the oracle."""
+    from fish_speech_b200.models.text2semantic.inference import generate_batch
+
+    cfg = O.tiny_config()
+    w = O.make_weights(cfg, seed=31, head_gain=8.0)
+    lens = [5, 17, 9, 30, 12]
+    prompts = [make_prompt(cfg, 100 + i, T) for i, T in enumerate(lens)]
+    n = 9
+    model = build_model(cfg, w, max_batch=len(lens))
+    outs = generate_batch(model=model, prompts=[p.cuda() for p in prompts], max_new_tokens=n, temperature=0.7,
+                          top_p=0.7, top_k=1)
+    solo = build_model(cfg, w, max_batch=1)
+    for i, p in enumerate(prompts):
+        st = O.setup(cfg, w)
+        ref = O.generate(st, p, n, temperature=0.7, top_p=0.7, top_k=1)
+        one = _gen(solo, p, n, temperature=0.7, top_p=0.7, top_k=1)
+        assert torch.equal(outs[i].cpu().to(torch.int32), one.to(torch.int32)), f"seq {i}: batch != solo"
+        assert torch.equal(one.to(torch.int32), ref), f"seq {i}: CUDA != oracle"
+
+
+def test_prefill_chunking_equals_single_pass():
+    """max_rows smaller than the prompt: time-split prefill must give the same continuation."""
+    cfg = O.tiny_config()
+    w = O.make_weights(cfg, seed=41, head_gain=8.0)
+    p = make_prompt(cfg, 41, 70)
+    a = _gen(build_model(cfg, w, max_rows=2048), p, 6, temperature=0.7, top_p=0.7, top_k=1)
+    b = _gen(build_model(cfg, w, max_rows=128), p, 6, temperature=0.7, top_p=0.7, top_k=1)  # 70 < 128: one pass
+    assert torch.equal(a, b)
+    st = O.setup(cfg, w)
+    assert torch.equal(a.to(torch.int32), O.generate(st, p, 6, temperature=0.7, top_p=0.7, top_k=1))
+
+
+def test_s2pro_layer_geometry_greedy():
+    """S2-Pro layer shapes (dim 2560, 32/8 heads x 128, I 9728, 10 codebooks x 4096) with few layers and a
+    reduced vocabulary so the CPU oracle finishes in seconds: greedy tokens identical."""
+    cfg = O.LMConfig(n_layer=2, n_fast_layer=1, vocab_size=8192, max_seq_len=256, semantic_begin_id=4000,
+                     semantic_end_id=8095, im_end_id=3999)
+    w = O.make_weights(cfg, seed=51, head_gain=6.0)
+    p = make_prompt(cfg, 51, 24)
+    st = O.setup(cfg, w)
+    ref = O.generate(st, p, 5, temperature=0.7, top_p=0.7, top_k=1)
+    got = _gen(build_model(cfg, w), p, 5, temperature=0.7, top_p=0.7, top_k=1)
+    assert torch.equal(got.to(torch.int32), ref), (got[:, 24:], ref[:, 24:])
+
+
+def test_stop_on_im_end_and_max_len_errors():
+    cfg = O.tiny_config()
+    w = O.make_weights(cfg, seed=61, head_gain=8.0)
+    # make <|im_end|> the only attractive row of the head: generation must stop right after emitting it
+    w["embeddings.weight"][cfg.im_end_id] = w["embeddings.weight"][cfg.im_end_id] * 0 + 0.5
+    p = make_prompt(cfg, 61, 10)
+    st = O.setup(cfg, w)
+    ref = O.generate(st, p, 20, temperature=0.7, top_p=0.7, top_k=1)
+    model = build_model(cfg, w)
+    got = _gen(model, p, 20, temperature=0.7, top_p=0.7, top_k=1)
+    assert got.shape == ref.shape and torch.equal(got.to(torch.int32), ref)
+    assert got.shape[1] < 10 + 20 and got[0, -1].item() == cfg.im_end_id
+    with pytest.raises(ValueError):
+        _gen(model, torch.zeros(cfg.num_codebooks + 1, cfg.max_seq_len, dtype=torch.long), 4)
+
+
+def test_stochastic_sampling_distribution():
+    """top-k / top-p / temperature sampling: empirical token frequencies of the first generated frame
+    follow the oracle's logits_to_probs distribution (our Philox stream differs from torch's)."""
+    from fish_speech_b200.models.text2semantic.inference import generate
+
+    cfg = O.tiny_config()
+    w = O.make_weights(cfg, seed=71, head_gain=2.5)
+    p = make_prompt(cfg, 71, 8)
+    st = O.setup(cfg, w)
+    logits, _ = O.forward_generate(st, p.view(1, cfg.num_codebooks + 1, -1), torch.arange(8))
+    dt = torch.bfloat16
+    probs = O.logits_to_probs((logits + O.semantic_logit_bias(cfg, dt))[0, -1], torch.tensor(0.9, dtype=dt),
+                              torch.tensor(0.8, dtype=dt), 5).float()
+    model = build_model(cfg, w)
+    N = 600
+    counts = torch.zeros(cfg.vocab_size)
+    for s in range(N):
+        out = generate(model=model, prompt=p.cuda(), max_new_tokens=1, temperature=0.9, top_p=0.8, top_k=5, seed=s)
+        counts[int(out[0, 8].item())] += 1
+    freq = counts / N
+    support = probs > 0
+    assert freq[~support].sum().item() == 0, "sampled a token outside the top-k/top-p support"
+    assert (freq - probs).abs().max().item() < 0.08, (freq[support], probs[support])
