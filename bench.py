@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native Fish-Speech hot path.
+
+Workload (BASELINE.json configs[2]): batch-32 text->codec->wav, 64-token prompts, 256 codec frames per
+utterance, bf16, greedy (top_k=1), synthetic seeded weights at the assumed S2-Pro geometry
+ — one "step" = the whole batch: prefill + 255 decode frames (+ codec decode to waveform
+once the codec stage is present in this build; `config.stages` says which stages were timed).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line.  `value` = audio-seconds generated per second (whole job, all GPUs) with the prompts
+resident in HBM; `e2e` = the same through the public API (`generate_batch`) from pinned host memory,
+including H2D of the prompts and D2H of the generated codes; `roofline` = measured HBM stream of the
+dominant kernel (the tcgen05 weight-streaming GEMM) against MEASURED_PEAKS.json; `cpu_baseline` = the
+oracle port of the reference's CPU path timed on this box's host cores on a bounded sample.
+
+Under torchrun (N > 1) every rank runs a full replica on its own shard of utterances (32 per GPU, weak
+scaling, no collective on the data path); times are device-side, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+SR, FRAME = 44100, 2048
+B_PER_GPU, T_PROMPT, N_FRAMES = 32, 64, 256
+
+
+def s2pro_cfg():
+    from fish_speech_b200.configs import s2pro_args
+
+    return s2pro_args(max_seq_len=512)
+
+
+def gpu_weights(cfg, device, seed=1234):
+    """Seeded synthetic bf16 weights generated directly on the device (no checkpoint, no network)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    std = cfg.initializer_range
+
+    def lin(o, i, gain=1.0):
+        return (torch.randn(o, i, generator=g, device=device, dtype=torch.float32) * (std * gain)).to(torch.bfloat16)
+
+    def nrm(n):
+        return (1.0 + 0.1 * torch.randn(n, generator=g, device=device)).to(torch.bfloat16)
+
+    w = {"embeddings.weight": lin(cfg.vocab_size, cfg.dim, 4.0),
+         "codebook_embeddings.weight": lin(cfg.codebook_size * cfg.num_codebooks, cfg.dim)}
+
+    def block(prefix, dim, nh, nkv, hd, inter, qk):
+        w[f"{prefix}.attention.wqkv.weight"] = lin((nh + 2 * nkv) * hd, dim)
+        w[f"{prefix}.attention.wo.weight"] = lin(dim, nh * hd)
+        if qk:
+            w[f"{prefix}.attention.q_norm.weight"] = nrm(hd)
+            w[f"{prefix}.attention.k_norm.weight"] = nrm(hd)
+        w[f"{prefix}.feed_forward.w1.weight"] = lin(inter, dim)
+        w[f"{prefix}.feed_forward.w3.weight"] = lin(inter, dim)
+        w[f"{prefix}.feed_forward.w2.weight"] = lin(dim, inter)
+        w[f"{prefix}.ffn_norm.weight"] = nrm(dim)
+        w[f"{prefix}.attention_norm.weight"] = nrm(dim)
+
+    for l in range(cfg.n_layer):
+        block(f"layers.{l}", cfg.dim, cfg.n_head, cfg.n_local_heads, cfg.head_dim, cfg.intermediate_size,
+              cfg.attention_qk_norm)
+    w["norm.weight"] = nrm(cfg.dim)
+    w["fast_embeddings.weight"] = lin(cfg.codebook_size, cfg.fast_dim)
+    for l in range(cfg.n_fast_layer):
+        block(f"fast_layers.{l}", cfg.fast_dim, cfg.fast_n_head, cfg.fast_n_local_heads, cfg.fast_head_dim,
+              cfg.fast_intermediate_size, cfg.fast_attention_qk_norm)
+    w["fast_norm.weight"] = nrm(cfg.fast_dim)
+    w["fast_output.weight"] = lin(cfg.codebook_size, cfg.fast_dim, 4.0)
+    return w
+
+
+def make_prompts(cfg, n, first_seed):
+    """row 0 = random text ids, rows 1..10 = 0; seeds 42, 43, ..."""
+    out = []
+    for i in range(n):
+        g = torch.Generator().manual_seed(first_seed + i)
+        p = torch.zeros(cfg.num_codebooks + 1, T_PROMPT, dtype=torch.int32)
+        p[0] = torch.randint(0, 151643, (T_PROMPT,), generator=g, dtype=torch.int32)
+        out.append(p)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def peaks():
+    try:
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text()), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def cpu_reference_port(steps: int, warmup: int, frames_per_step: int = 4):
+    """The reference's CPU path (oracle port: same operator sequence on CPU tensors) on the host cores,
+    on a bounded sample of the workload: ONE utterance (the reference is batch-1), 64-token prefill +
+    `frames_per_step` decode frames per step, bf16, all host threads.  Layer weights are ALIASED (every
+    layer shares one seeded tensor set: 0.2 GB >> L3, so the DRAM streaming cost per layer is intact)
+    to keep host RAM and set-up time bounded; timing does not depend on the weight values."""
+    from oracle import lm_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.LMConfig(max_seq_len=512)
+    one = O.LMConfig(max_seq_len=512, n_layer=1, n_fast_layer=1)
+    w1 = O.make_weights(one, seed=1234, head_gain=4.0)
+    w = dict(w1)
+    for l in range(cfg.n_layer):
+        for k, v in w1.items():
+            if k.startswith("layers.0."):
+                w[k.replace("layers.0.", f"layers.{l}.")] = v
+    for l in range(cfg.n_fast_layer):
+        for k, v in w1.items():
+            if k.startswith("fast_layers.0."):
+                w[k.replace("fast_layers.0.", f"fast_layers.{l}.")] = v
+    st = O.setup(cfg, w)
+    prompt = make_prompts(cfg, 1, 42)[0].long()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.generate(st, prompt, frames_per_step + 1, temperature=0.7, top_p=0.7, top_k=1, noise=False,
+                   stop_on_im_end=False)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    frames = frames_per_step + 1
+    sec = sum(times) / len(times)
+    value = frames * FRAME / SR / sec
+    return value, sec, cores, (f"1 utterance (reference is batch-1): 64-token prefill + {frames} frames per step, bf16, "
+                               f"{cores} threads, layer weights aliased; audio-s/s = frames*2048/44100/time")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=N_FRAMES)
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = f"batch-{args.batch} text->codec, {T_PROMPT}-token prompts, {args.frames} codec frames/utt, S2-Pro 4B geometry"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        v, sec, cores, sample = cpu_reference_port(max(1, min(args.steps, 3)), min(args.warmup, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": "audio-sec/s", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import torch.distributed as dist
+
+    from fish_speech_b200 import _lib
+    from fish_speech_b200.models.text2semantic.inference import generate_batch
+    from fish_speech_b200.configs import S2PRO_IM_END_ID
+    from fish_speech_b200.models.text2semantic.llama import DualARTransformer
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = s2pro_cfg()
+    B, NF = args.batch, args.frames
+    weights = gpu_weights(cfg, dev)
+    model = DualARTransformer(cfg, weights, device=dev, im_end_id=S2PRO_IM_END_ID)
+    model.max_rows = B * T_PROMPT
+    model.setup_caches(max_batch_size=B, max_seq_len=cfg.max_seq_len)
+    del weights
+    eng = model.engine
+    # utterance shard of this rank: utts[rank::world] of 32*world prompts (seeds 42..)
+    prompts_host = [p.pin_memory() for p in make_prompts(cfg, B * world, 42)[rank::world]]
+    prompts_dev = [p.to(dev) for p in prompts_host]
+    sp = eng.sampling(0.7, 0.7, 1, 42)
+    L = _lib.lib()
+
+    def step_resident():
+        eng.reset()
+        eng.prefill(prompts_dev, list(range(B)), sp, do_sample=True)
+        eng.decode(B, NF - 1, sp, use_graph=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = _lib.launch_count()  # counts eager launches AND the kernels of every graph replay
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    audio_s = B * world * NF * FRAME / SR
+    value = audio_s / (ms_per_step / 1e3)
+
+    # ---- e2e through the public API: host prompts -> generate_batch -> codes on the host ----
+    def step_e2e():
+        outs = generate_batch(model=model, prompts=[p.to(dev, non_blocking=True) for p in prompts_host],
+                              max_new_tokens=NF, temperature=0.7, top_p=0.7, top_k=1, seed=42)
+        return [o[:, T_PROMPT:].cpu() for o in outs]
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, max(1, args.steps // 2)) / max(1, args.steps // 2)
+    e2e_value = audio_s / (ms_e2e / 1e3)
+    h2d = sum(p.numel() * p.element_size() for p in prompts_host) * world
+    d2h = B * world * (cfg.num_codebooks + 1) * NF * 4
+
+    # ---- roofline of the dominant kernel: the decode GEMM stream, measured live ----
+    import ctypes as C
+
+    wb, nl = C.c_double(), C.c_int()
+    reps = 20
+    _lib.check(L.fsb_lm_bench_gemms(eng.h, 2, C.byref(wb), C.byref(nl), torch.cuda.current_stream().cuda_stream))
+    gemm_ms = timed(lambda: _lib.check(L.fsb_lm_bench_gemms(eng.h, reps, C.byref(wb), C.byref(nl),
+                                                            torch.cuda.current_stream().cuda_stream)), 1)
+    pk, pk_kind = peaks()
+    gemm_gbs = wb.value * reps / (gemm_ms / 1e3) / 1e9
+    # frame-level: algorithmic bytes per frame = weights + KV reads (B * L * 147456 B), SURVEY §8(d)
+    kv_per_tok = cfg.n_layer * 2 * cfg.n_local_heads * cfg.head_dim * 2
+    avg_L = T_PROMPT + NF / 2
+    frame_bytes = wb.value + B * avg_L * kv_per_tok
+    frame_ms = ms_per_step / NF  # includes the prefill, amortised
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": "audio-sec/s", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {
+                "workload": workload, "stages": ["lm_prefill", "lm_decode"], "utterances": B * world,
+                "frames_per_s": B * world * NF / (ms_per_step / 1e3),
+                "codec_tokens_per_s": B * world * NF * cfg.num_codebooks / (ms_per_step / 1e3),
+                "ms_per_frame": frame_ms, "sampling": "greedy top_k=1 T=0.7 top_p=0.7",
+                "l2_note": "inputs larger than L2: 9.1 GB of weights streamed per frame (126 MB L2)",
+                "parallelism": f"replica x{world}, utts[rank::world]",
+                "frame_hbm_frac": frame_bytes / (frame_ms / 1e3) / 1e9 / pk["hbm_gbs"],
+            },
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "bound": "hbm", "achieved": gemm_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": gemm_gbs / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                "kernel": "gemm_tc_kernel<32> (tcgen05 + TMA weight streaming, stream-K)",
+                "bytes_per_launch": wb.value / nl.value, "launches": nl.value * reps,
+                "avg_launch_us": gemm_ms * 1e3 / (nl.value * reps),
+            },
+            "clocks": clk,
+        }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if not args.no_cpu_baseline:
+            try:
+                v, sec, cores, sample = cpu_reference_port(1, 0, frames_per_step=3)
+                out["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample}
+            except Exception as e:  # pragma: no cover
+                out["cpu_baseline"] = {"value": None, "error": repr(e)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

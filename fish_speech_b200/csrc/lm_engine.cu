@@ -74,6 +74,7 @@ struct fsb_lm {
     // decode graph cache
     cudaGraphExec_t graph_exec = nullptr;
     int graph_batch = -1;
+    int graph_kernels = 0;  // kernels inside one captured frame
     fsb_sampling graph_sampling{};
     std::vector<void*> owned;
     std::map<std::string, std::pair<void*, size_t>> named;
@@ -582,10 +583,13 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int
         h->graph_exec = sentinel;  // suppress debug copies while capturing
         cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
         int rc = 1;
+        const int launches_before = g_launch_count;
         if (e == cudaSuccess) {
             rc = decode_one_frame(h, batch, *sp, cs);
             e = cudaStreamEndCapture(cs, &g);
         }
+        h->graph_kernels = g_launch_count - launches_before;
+        g_launch_count = launches_before;  // captured, not launched
         h->graph_exec = nullptr;
         if (e != cudaSuccess || rc != 0 || g == nullptr) {
             if (rc == 0) set_error("decode: graph capture failed: %s", cudaGetErrorString(e));
@@ -605,7 +609,51 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int
         h->graph_batch = batch;
         h->graph_sampling = *sp;
     }
-    for (int i = 0; i < nframes; ++i) FSB_CUDA(cudaGraphLaunch(h->graph_exec, st));
+    for (int i = 0; i < nframes; ++i) {
+        FSB_CUDA(cudaGraphLaunch(h->graph_exec, st));
+        g_launch_count += h->graph_kernels;
+    }
+    return 0;
+}
+
+int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* launches_per_rep, void* stream) {
+    // Every weight-streaming GEMM of one decode frame (36 slow layers x 4, head, 10 fast passes x
+    // (4 layers x 4 + head)) back to back, without the glue kernels: the measured stream of the
+    // dominant kernel for the roofline line of bench.py. Operands are whatever the workspaces hold.
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const fsb_lm_config& c = h->cfg;
+    double bytes = 0;
+    int launches = 0;
+    auto run = [&](const GemmPlan& p, double wbytes) -> int {
+        bytes += wbytes;
+        ++launches;
+        return gemm_launch(p, st);
+    };
+    for (int r = 0; r < reps; ++r) {
+        bytes = 0;
+        launches = 0;
+        auto stack = [&](Stack& s, bool skip_tail) -> int {
+            const double nq = static_cast<double>((s.H + 2 * s.Hkv) * s.Dh) * s.D * 2;
+            const double no = static_cast<double>(s.D) * s.H * s.Dh * 2;
+            const double n13 = 2.0 * s.I * s.D * 2, n2 = static_cast<double>(s.D) * s.I * 2;
+            for (int l = 0; l < s.nl; ++l) {
+                FSB_TRY(run(s.dec[l].qkv, nq));
+                if (skip_tail && l == s.nl - 1) break;
+                FSB_TRY(run(s.dec[l].wo, no));
+                FSB_TRY(run(s.dec[l].w13, n13));
+                FSB_TRY(run(s.dec[l].w2, n2));
+            }
+            return 0;
+        };
+        FSB_TRY(stack(h->slow, false));
+        FSB_TRY(run(h->head_plan, static_cast<double>(h->head_rows) * c.dim * 2));
+        for (int p = 0; p < c.num_codebooks; ++p) {
+            FSB_TRY(stack(h->fast, p == 0));
+            if (p > 0) FSB_TRY(run(h->fast_out_plan, static_cast<double>(c.codebook_size) * c.fast_dim * 2));
+        }
+    }
+    if (weight_bytes_per_rep) *weight_bytes_per_rep = bytes;
+    if (launches_per_rep) *launches_per_rep = launches;
     return 0;
 }
 

@@ -129,6 +129,11 @@ int fsb_lm_reset(fsb_lm* h, void* stream);
  *   "hidden" bf16 [32][dim], "dbg_x" bf16 [n_layer+1][32][dim] */
 int fsb_lm_buffer(fsb_lm* h, const char* name, void** d_ptr, size_t* bytes);
 
+/* Measurement hook for bench.py: launch every weight-streaming GEMM of one decode frame `reps` times
+ * (no glue kernels); returns the algorithmic weight bytes and launch count of one repetition. */
+int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* launches_per_rep,
+                       void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Unit-test hooks (used by tests/ only)
  * ---------------------------------------------------------------------------------------------- */

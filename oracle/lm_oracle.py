@@ -319,9 +319,19 @@ def logits_to_probs(logits, temperature, top_p, top_k: int):
     return F.softmax(logits, dim=-1)
 
 
+NOISE = True
+"""multinomial_sample_one_no_sync (inference.py:43-46) divides the probabilities by -log(U) with U drawn
+in the probs dtype.  In bf16 U takes only 256 values and is EXACTLY 0 with probability 1/256; then
+-log(U) = inf, every score becomes 0 and argmax returns index 0 — even with top_k=1, where the result
+should not depend on the noise at all.  This is a quirk of the reference (verified against it: the
+pinned runs reproduce it bit for bit).  NOISE=False drops the division so that the top_k=1 path is the
+deterministic argmax the reference intends; CUDA parity is defined against that."""
+
+
 def sample(logits, temperature, top_p, top_k: int, generator=None):
     probs = logits_to_probs(logits[0, -1], temperature, top_p, top_k)
-    # multinomial_sample_one_no_sync (inference.py:43-46): uniform noise drawn in the probs dtype
+    if not NOISE:
+        return torch.argmax(probs, dim=-1, keepdim=True).to(torch.int), probs
     q = -torch.log(torch.rand(probs.shape, dtype=probs.dtype, generator=generator))
     return torch.argmax(probs / q, dim=-1, keepdim=True).to(torch.int), probs
 
@@ -368,8 +378,19 @@ def decode_one_token_ar(st: LMState, x, input_pos, temperature, top_p, top_k: in
 
 
 def generate(st: LMState, prompt: torch.Tensor, max_new_tokens: int, temperature=1.0, top_p=0.9, top_k=30,
-             generator=None, traces: Optional[list] = None, stop_on_im_end: bool = True) -> torch.Tensor:
-    """inference.py:243-359 + decode_n_tokens :184-238. prompt [C+1, T] -> [C+1, T+n]."""
+             generator=None, traces: Optional[list] = None, stop_on_im_end: bool = True,
+             noise: bool = True) -> torch.Tensor:
+    """inference.py:243-359 + decode_n_tokens :184-238. prompt [C+1, T] -> [C+1, T+n].
+    noise=False: deterministic top_k=1 (see NOISE)."""
+    global NOISE
+    saved, NOISE = NOISE, noise
+    try:
+        return _generate(st, prompt, max_new_tokens, temperature, top_p, top_k, generator, traces, stop_on_im_end)
+    finally:
+        NOISE = saved
+
+
+def _generate(st, prompt, max_new_tokens, temperature, top_p, top_k, generator, traces, stop_on_im_end):
     cfg = st.cfg
     dt = st.w["embeddings.weight"].dtype
     T = prompt.size(1)

@@ -57,18 +57,29 @@ def run_lm_case(name, over, seed, head_gain, T, n, top_k, temp, top_p):
     w = O.make_weights(cfg, seed=seed, head_gain=head_gain)
     model = R.reference_lm(cfg, w)
     prompt = make_prompt(cfg, seed, T)
-    torch.manual_seed(seed)
-    ref = ref_inf.generate(model=model, prompt=prompt, max_new_tokens=n, audio_masks=None, audio_parts=None,
-                           temperature=temp, top_p=top_p, top_k=top_k).to(torch.int32)
-    st = O.setup(cfg, w)
-    traces = []
-    torch.manual_seed(seed)
-    got = O.generate(st, prompt, n, temperature=temp, top_p=top_p, top_k=top_k, traces=traces)
-    assert torch.equal(ref, got), f"{name}: oracle differs from the reference"
+    rng_seed = seed
+    while True:
+        torch.manual_seed(rng_seed)
+        ref = ref_inf.generate(model=model, prompt=prompt, max_new_tokens=n, audio_masks=None, audio_parts=None,
+                               temperature=temp, top_p=top_p, top_k=top_k).to(torch.int32)
+        st = O.setup(cfg, w)
+        traces = []
+        torch.manual_seed(rng_seed)
+        got = O.generate(st, prompt, n, temperature=temp, top_p=top_p, top_k=top_k, traces=traces)
+        assert torch.equal(ref, got), f"{name}: oracle differs from the reference"
+        if top_k != 1:
+            break
+        # greedy cases: keep an RNG seed for which the reference's bf16 noise never hit U == 0
+        # (see lm_oracle.NOISE), so the fixture is the deterministic argmax sequence.
+        clean = O.generate(O.setup(cfg, w), prompt, n, temperature=temp, top_p=top_p, top_k=top_k, noise=False)
+        if torch.equal(clean, ref):
+            break
+        print(f"{name}: rng seed {rng_seed} hits the U==0 quirk, trying the next one")
+        rng_seed += 1000
     np.savez_compressed(
         GOLD / f"{name}.npz",
         config=np.array(repr(over)), weight_seed=seed, head_gain=head_gain, prompt=prompt.numpy(),
-        new_frames=n, top_k=top_k, temperature=temp, top_p=top_p, rng_seed=seed,
+        new_frames=n, top_k=top_k, temperature=temp, top_p=top_p, rng_seed=rng_seed,
         ref_tokens=ref.numpy(),
         ref_slow_logits=torch.stack([t["slow_logits"] for t in traces]).numpy().astype(np.float32),
     )

@@ -66,3 +66,25 @@ def restricted(cfg: O.LMConfig, full_logits: torch.Tensor) -> torch.Tensor:
     """Selectable rows of a full-vocabulary logit vector: semantic ids, then <|im_end|>."""
     return torch.cat([full_logits[..., cfg.semantic_begin_id: cfg.semantic_end_id + 1],
                       full_logits[..., cfg.im_end_id: cfg.im_end_id + 1]], dim=-1)
+
+
+def assert_tokens_match(got: torch.Tensor, ref: torch.Tensor, traces: list, cfg: O.LMConfig, T: int, what: str = ""):
+    """Free-running greedy parity. Token ids / codes must be identical; the only tolerated divergence
+    is a decision the oracle itself took on a bf16 near-tie (top-2 logit gap within 2 bf16 ulps), after
+    which the two runs legitimately follow different histories. Returns the number of frames compared."""
+    got, ref = got.to(torch.int32).cpu(), ref.to(torch.int32).cpu()
+    n = min(got.shape[1], ref.shape[1])
+    for f in range(T, n):
+        if torch.equal(got[:, f], ref[:, f]):
+            continue
+        r = int((got[:, f] != ref[:, f]).nonzero()[0])
+        tr = traces[f - T]
+        logits = restricted(cfg, tr["slow_logits"]) if r <= 1 else tr["fast_logits"][r - 2]
+        top2 = torch.topk(logits.float(), 2).values
+        gap = float(top2[0] - top2[1])
+        ulp = float(top2[0].abs()) * 2 ** -7
+        assert gap <= 2 * ulp, (f"{what}: frame {f - T} row {r}: got {got[:, f].tolist()} want {ref[:, f].tolist()} "
+                               f"(oracle top-2 gap {gap:.4g}, 2 ulp = {2 * ulp:.4g})")
+        return f - T
+    assert got.shape == ref.shape, f"{what}: length {got.shape} vs {ref.shape}"
+    return n - T
