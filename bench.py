@@ -136,6 +136,19 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def usable_cores() -> int:
+    """Host cores this process can really use: the affinity mask capped by the cgroup CPU quota (GPU
+    boxes expose 128 hardware threads but a quota of 16; an oversized OpenMP team thrashes)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(p))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference_port(steps: int, warmup: int, frames_per_step: int = 4):
     """The reference's CPU path (oracle port: same operator sequence on CPU tensors) on the host cores,
     on a bounded sample of the workload: ONE utterance (the reference is batch-1), 64-token prefill +
@@ -144,7 +157,7 @@ def cpu_reference_port(steps: int, warmup: int, frames_per_step: int = 4):
     to keep host RAM and set-up time bounded; timing does not depend on the weight values."""
     from oracle import lm_oracle as O
 
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     cfg = O.LMConfig(max_seq_len=512)
     one = O.LMConfig(max_seq_len=512, n_layer=1, n_fast_layer=1)
@@ -184,6 +197,7 @@ def main():
     ap.add_argument("--frames", type=int, default=N_FRAMES)
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="run the timed step once and exit (for ncu)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -258,6 +272,10 @@ def main():
 
     for _ in range(args.warmup):
         step_resident()
+    if args.profile_only:
+        step_resident()
+        torch.cuda.synchronize()
+        return
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()

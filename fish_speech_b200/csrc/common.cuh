@@ -153,9 +153,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug becomes a trap (launch failure) instead of a hung GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
+        if (clock64() - t0 > 4000000000ll) {  // ~2 s at ~2 GHz
             printf("fsb: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n",
                    blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
             __trap();
