@@ -37,6 +37,7 @@ int fsb_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream) {
 // Reduce stream-K partial sums: out[j][i] = sum_s ws[s][j][i]
 static __global__ void reduce_parts_kernel(const float* ws, long long slot_stride, const int* nparts,
                                            float* out, int m, int n) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (i >= m || j >= n) return;
     const int np = nparts[i >> 7];

@@ -50,6 +50,34 @@ extern thread_local int g_launch_count;  // kernels launched by this thread (ben
         FSB_CUDA(cudaGetLastError());                                                             \
     } while (0)
 
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may start while its
+// predecessor in the stream is still running; every kernel launched this way executes
+// griddepcontrol.wait before it touches anything a predecessor produces (or still reads).
+bool pdl_enabled();
+template <typename... Args>
+static inline cudaError_t launch_pdl(const void* kernel, dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t st, Args... args) {
+    void* kargs[] = {reinterpret_cast<void*>(&args)...};
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelExC(&cfg, kernel, kargs);
+}
+#define FSB_LAUNCH(kernel, grid, block, smem, st, ...)                                            \
+    do {                                                                                          \
+        ::fsb::g_launch_count++;                                                                  \
+        FSB_CUDA(::fsb::launch_pdl(reinterpret_cast<const void*>(kernel), grid, block, smem, st,  \
+                                   __VA_ARGS__));                                                 \
+    } while (0)
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 

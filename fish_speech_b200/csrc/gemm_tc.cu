@@ -219,23 +219,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
+    pdl_launch_dependents();  // let the consumer kernel get resident; it blocks in griddepcontrol.wait
     if (warp == 4) {
         // ===== TMA producer: the ring keeps flowing across item boundaries =====
+        // Operand A (weights when a_static) does not depend on the upstream kernel: its tiles for the
+        // whole ring are requested BEFORE griddepcontrol.wait, so the HBM stream of this GEMM starts
+        // while the previous kernel (a small consumer kernel) is still running. Operand B (the
+        // activations that kernel produces) is only fetched after the wait.
         if (lane == 0) {
             int it = 0;
+            int pre = 0;  // ring slots whose A tile was requested early
+            bool waited = false;
+            if (p.a_static) {
+                int n = item_begin, kb = 0, i0 = 0, j0 = 0, kb0 = 0, kb1 = 0, slot = 0;
+                if (n < item_end) {
+                    get_item(n, i0, j0, kb0, kb1, slot);
+                    kb = kb0;
+                }
+                while (n < item_end && pre < stages) {
+                    const int s = pre;
+                    mbar_expect_tx(full0 + 8u * s, kStageBytes);
+                    const int tap = kb / p.kb_per_tap;
+                    const int kc = (kb - tap * p.kb_per_tap) * kBlockK;
+                    tma_load_3d(tiles + static_cast<uint32_t>(s) * kStageBytes, &tmA, full0 + 8u * s,
+                                p.a_tapk * tap + kc, i0 + p.a_shift[tap], p.a_batched ? z : 0, p.a_hint);
+                    ++pre;
+                    if (++kb >= kb1) {
+                        if (++n < item_end) {
+                            get_item(n, i0, j0, kb0, kb1, slot);
+                            kb = kb0;
+                        }
+                    }
+                }
+            }
+            pdl_wait();
+            waited = true;
+            (void)waited;
             for (int n = item_begin; n < item_end; ++n) {
                 int i0, j0, kb0, kb1, slot;
                 get_item(n, i0, j0, kb0, kb1, slot);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = static_cast<uint32_t>(it / stages) & 1u;
-                    mbar_wait(empty0 + 8u * s, ph ^ 1u);
-                    mbar_expect_tx(full0 + 8u * s, kStageBytes);
                     const int tap = kb / p.kb_per_tap;
                     const int kc = (kb - tap * p.kb_per_tap) * kBlockK;
                     const uint32_t a_dst = tiles + static_cast<uint32_t>(s) * kStageBytes;
-                    tma_load_3d(a_dst, &tmA, full0 + 8u * s, p.a_tapk * tap + kc,
-                                i0 + p.a_shift[tap], p.a_batched ? z : 0, p.a_hint);
+                    if (it >= pre) {
+                        mbar_wait(empty0 + 8u * s, ph ^ 1u);
+                        mbar_expect_tx(full0 + 8u * s, kStageBytes);
+                        tma_load_3d(a_dst, &tmA, full0 + 8u * s, p.a_tapk * tap + kc,
+                                    i0 + p.a_shift[tap], p.a_batched ? z : 0, p.a_hint);
+                    }
                     tma_load_3d(a_dst + kATileBytes, &tmB, full0 + 8u * s, p.b_tapk * tap + kc,
                                 j0 + p.b_shift[tap], p.b_batched ? z : 0, p.b_hint);
                 }
@@ -372,8 +406,7 @@ int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
         FSB_TRY(gemm_init());
         attr_set = true;
     }
-    gemm_tc_kernel<BN><<<plan.grid, kThreads, plan.smem, stream>>>(plan.tmA, plan.tmB, plan.p);
-    FSB_LAUNCH_CHECK();
+    FSB_LAUNCH(gemm_tc_kernel<BN>, plan.grid, dim3(kThreads), plan.smem, stream, plan.tmA, plan.tmB, plan.p);
     return 0;
 }
 

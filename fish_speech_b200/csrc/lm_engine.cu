@@ -105,6 +105,7 @@ int make_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const 
     p.kb_per_tap = kblocks;
     p.num_taps = 1;
     p.a_hint = kEvictFirst;  // weights are streamed once per step (>> L2)
+    p.a_static = 1;
     p.b_hint = kEvictLast;   // the activation tile is re-read by every CTA
     p.rows_i = n_out;
     p.mode = 0;

@@ -6,11 +6,23 @@ namespace fsb {
 
 namespace {
 
+// Sum of the stream-K partials of one output element, always in slot order (deterministic and
+// independent of the batch). Loads are issued four at a time so the L2 latencies overlap.
 __device__ __forceinline__ float sum_parts(const Partials& P, int j, int i) {
-    const int np = P.nparts ? P.nparts[i >> 7] : 1;
+    const int np = P.nparts ? __ldg(P.nparts + (i >> 7)) : 1;
     const float* p = P.ws + static_cast<size_t>(j) * P.ld + i;
-    float s = p[0];
-    for (int q = 1; q < np; ++q) s += p[static_cast<size_t>(q) * P.slot_stride];
+    const size_t ss = static_cast<size_t>(P.slot_stride);
+    float s = 0.f;
+    for (int q = 0; q < np; q += 4) {
+        const float a0 = p[static_cast<size_t>(q) * ss];
+        const float a1 = q + 1 < np ? p[static_cast<size_t>(q + 1) * ss] : 0.f;
+        const float a2 = q + 2 < np ? p[static_cast<size_t>(q + 2) * ss] : 0.f;
+        const float a3 = q + 3 < np ? p[static_cast<size_t>(q + 3) * ss] : 0.f;
+        s += a0;
+        s += a1;
+        s += a2;
+        s += a3;
+    }
     return s;
 }
 
@@ -18,6 +30,8 @@ __device__ __forceinline__ float sum_parts(const Partials& P, int j, int i) {
 // embed: llama.py:399-420
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_kernel(EmbedArgs a, float inv_div) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x;
     const int* t = a.tokens + static_cast<size_t>(row) * (a.C + 1);
     int tok = t[0];
@@ -41,10 +55,12 @@ __global__ void embed_kernel(EmbedArgs a, float inv_div) {
 // ------------------------------------------------------------------------------------------------
 // residual add + fish RMSNorm
 // ------------------------------------------------------------------------------------------------
-constexpr int kRnThreads = 256;
-constexpr int kRnMaxPer = 16;  // D <= 4096
+constexpr int kRnThreads = 1024;
+constexpr int kRnMaxPer = 4;  // D <= 4096
 
 __global__ void __launch_bounds__(kRnThreads) resid_norm_kernel(ResidNormArgs a, int gstride) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[33];
     const int row = blockIdx.x;
     const int grow = a.gather_map ? a.gather_map[row] : row;
@@ -81,6 +97,8 @@ __global__ void __launch_bounds__(kRnThreads) resid_norm_kernel(ResidNormArgs a,
 }
 
 __global__ void linear_out_kernel(LinearOutArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.N) return;
@@ -93,6 +111,8 @@ __global__ void linear_out_kernel(LinearOutArgs a) {
 // q/k/v post-processing: llama.py:891-911
 // ------------------------------------------------------------------------------------------------
 __global__ void qkv_prep_kernel(QkvPrepArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[33];
     const int row = blockIdx.x, head = blockIdx.y;
     const int t = threadIdx.x;  // pair index, Dh/2 threads
@@ -140,11 +160,13 @@ __global__ void qkv_prep_kernel(QkvPrepArgs a) {
 // ------------------------------------------------------------------------------------------------
 // length-aware GQA attention over the KV cache (one query token per CTA, all G heads of a KV group)
 // ------------------------------------------------------------------------------------------------
-constexpr int kAttnThreads = 128;
+constexpr int kAttnThreads = 256;
 constexpr int kAttnWarps = kAttnThreads / 32;
 
 template <int DH, int G>
 __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnArgs a, float scale, int lcap) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];
     float* qs = sm;                      // [G][DH]
     float* sc = qs + G * DH;             // [G][lcap]
@@ -174,21 +196,30 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnArgs a, float sc
     for (int gg = 0; gg < G; ++gg)
 #pragma unroll
         for (int e = 0; e < 8; ++e) qr[gg][e] = qs[gg * DH + li * 8 + e];
-    for (int pb = warp * RPW; pb < L; pb += kAttnWarps * RPW) {
-        const int p = pb + sub;
-        const bool ok = p < L;
-        uint4 u = make_uint4(0, 0, 0, 0);
-        if (ok) u = *reinterpret_cast<const uint4*>(kc + static_cast<size_t>(p) * DH + li * 8);
-        float kf[8] = {bf_lo(u.x), bf_hi(u.x), bf_lo(u.y), bf_hi(u.y),
-                       bf_lo(u.z), bf_hi(u.z), bf_lo(u.w), bf_hi(u.w)};
+    constexpr int UNR = 4;  // independent 16-byte loads in flight per lane
+    for (int pb = warp * RPW * UNR; pb < L; pb += kAttnWarps * RPW * UNR) {
+        uint4 u[UNR];
 #pragma unroll
-        for (int gg = 0; gg < G; ++gg) {
-            float d = 0.f;
+        for (int j = 0; j < UNR; ++j) {
+            const int p = pb + j * RPW + sub;
+            u[j] = make_uint4(0, 0, 0, 0);
+            if (p < L) u[j] = *reinterpret_cast<const uint4*>(kc + static_cast<size_t>(p) * DH + li * 8);
+        }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) d += qr[gg][e] * kf[e];
+        for (int j = 0; j < UNR; ++j) {
+            const int p = pb + j * RPW + sub;
+            const bool ok = p < L;
+            const float kf[8] = {bf_lo(u[j].x), bf_hi(u[j].x), bf_lo(u[j].y), bf_hi(u[j].y),
+                                 bf_lo(u[j].z), bf_hi(u[j].z), bf_lo(u[j].w), bf_hi(u[j].w)};
 #pragma unroll
-            for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-            if (ok && li == 0) sc[gg * lcap + p] = a.bf16_math ? rbf(rbf(d) * scale) : d * scale;
+            for (int gg = 0; gg < G; ++gg) {
+                float d = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d += qr[gg][e] * kf[e];
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                if (ok && li == 0) sc[gg * lcap + p] = a.bf16_math ? rbf(rbf(d) * scale) : d * scale;
+            }
         }
     }
     __syncthreads();
@@ -221,20 +252,34 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnArgs a, float sc
     for (int gg = 0; gg < G; ++gg)
 #pragma unroll
         for (int e = 0; e < DPL; ++e) acc[gg][e] = 0.f;
-    for (int p = warp; p < L; p += kAttnWarps) {
-        float vf[DPL];
-        if (DPL == 4) {
-            const uint2 u = *reinterpret_cast<const uint2*>(vc + static_cast<size_t>(p) * DH + lane * 4);
-            vf[0] = bf_lo(u.x); vf[1] = bf_hi(u.x); vf[2 % DPL] = bf_lo(u.y); vf[3 % DPL] = bf_hi(u.y);
-        } else {
-            const uint32_t u = *reinterpret_cast<const uint32_t*>(vc + static_cast<size_t>(p) * DH + lane * 2);
-            vf[0] = bf_lo(u); vf[1] = bf_hi(u);
+    for (int pb = warp; pb < L; pb += kAttnWarps * UNR) {
+        float vf[UNR][DPL];
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int p = pb + j * kAttnWarps;
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) vf[j][e] = 0.f;
+            if (p < L) {
+                if (DPL == 4) {
+                    const uint2 u2 = *reinterpret_cast<const uint2*>(vc + static_cast<size_t>(p) * DH + lane * 4);
+                    vf[j][0] = bf_lo(u2.x); vf[j][1] = bf_hi(u2.x); vf[j][2 % DPL] = bf_lo(u2.y); vf[j][3 % DPL] = bf_hi(u2.y);
+                } else {
+                    const uint32_t u1 = *reinterpret_cast<const uint32_t*>(vc + static_cast<size_t>(p) * DH + lane * 2);
+                    vf[j][0] = bf_lo(u1); vf[j][1] = bf_hi(u1);
+                }
+            }
         }
 #pragma unroll
-        for (int gg = 0; gg < G; ++gg) {
-            const float w = sc[gg * lcap + p];
+        for (int j = 0; j < UNR; ++j) {
+            const int p = pb + j * kAttnWarps;
+            if (p < L) {
 #pragma unroll
-            for (int e = 0; e < DPL; ++e) acc[gg][e] += w * vf[e];
+                for (int gg = 0; gg < G; ++gg) {
+                    const float w = sc[gg * lcap + p];
+#pragma unroll
+                    for (int e = 0; e < DPL; ++e) acc[gg][e] += w * vf[j][e];
+                }
+            }
         }
     }
 #pragma unroll
@@ -252,6 +297,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnArgs a, float sc
 }
 
 __global__ void swiglu_kernel(SwigluArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.I) return;
@@ -320,6 +367,8 @@ __device__ __forceinline__ ArgMax block_argmax(ArgMax x, ArgMax* red) {
 }
 
 __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float lg[kSampleMaxN];
     __shared__ ArgMax red[33];
     __shared__ float fred[33];
@@ -448,6 +497,8 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
 }
 
 __global__ void frame_end_kernel(FrameEndArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x;
     const int slot = a.row_slot ? a.row_slot[row] : row;
     const int f = a.n_out[slot];
@@ -463,9 +514,13 @@ __global__ void frame_end_kernel(FrameEndArgs a) {
             a.pos[slot] = a.pos[slot] + 1;
     }
 }
-__global__ void step_inc_kernel(unsigned long long* step) { *step += 1; }
+__global__ void step_inc_kernel(unsigned long long* step) {     pdl_launch_dependents();
+    pdl_wait();
+*step += 1; }
 
 __global__ void gather_rows_kernel(const __nv_bfloat16* src, const int* idx, __nv_bfloat16* dst, int D) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x;
     const size_t s = static_cast<size_t>(idx[row]) * D, d = static_cast<size_t>(row) * D;
     for (int e = threadIdx.x; e < D; e += blockDim.x) dst[d + e] = src[s + e];
@@ -475,8 +530,7 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* src, const int* idx, __n
 
 int launch_embed(const EmbedArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
-    embed_kernel<<<a.rows, 256, 0, st>>>(a, sqrtf(static_cast<float>(a.C + 1)));
-    FSB_LAUNCH_CHECK();
+    FSB_LAUNCH(embed_kernel, dim3(a.rows), dim3(256), 0, st, a, sqrtf(static_cast<float>(a.C + 1)));
     return 0;
 }
 
@@ -485,23 +539,20 @@ int launch_resid_norm(const ResidNormArgs& a, cudaStream_t st) { return launch_r
 int launch_resid_norm_g(const ResidNormArgs& a, int gather_stride, cudaStream_t st) {
     if (a.rows <= 0) return 0;
     FSB_CHECK(a.D <= kRnThreads * kRnMaxPer, "resid_norm: D=%d too large", a.D);
-    resid_norm_kernel<<<a.rows, kRnThreads, 0, st>>>(a, gather_stride);
-    FSB_LAUNCH_CHECK();
+    FSB_LAUNCH(resid_norm_kernel, dim3(a.rows), dim3(kRnThreads), 0, st, a, gather_stride);
     return 0;
 }
 
 int launch_linear_out(const LinearOutArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
-    linear_out_kernel<<<dim3(cdiv(a.N, 256), a.rows), 256, 0, st>>>(a);
-    FSB_LAUNCH_CHECK();
+    FSB_LAUNCH(linear_out_kernel, dim3(cdiv(a.N, 256), a.rows), dim3(256), 0, st, a);
     return 0;
 }
 
 int launch_qkv_prep(const QkvPrepArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
     FSB_CHECK(a.Dh % 64 == 0 && a.Dh <= 256, "qkv_prep: head_dim %d unsupported", a.Dh);
-    qkv_prep_kernel<<<dim3(a.rows, a.H + 2 * a.Hkv), a.Dh / 2, 0, st>>>(a);
-    FSB_LAUNCH_CHECK();
+    FSB_LAUNCH(qkv_prep_kernel, dim3(a.rows, a.H + 2 * a.Hkv), dim3(a.Dh / 2), 0, st, a);
     return 0;
 }
 
@@ -512,8 +563,7 @@ static int launch_attn_t(const AttnArgs& a, cudaStream_t st) {
                          static_cast<size_t>(kAttnWarps) * G * DH) * sizeof(float);
     FSB_CHECK(smem <= 200 * 1024, "attention: context %d too long for the shared-memory score buffer", lcap);
     const float scale = 1.0f / sqrtf(static_cast<float>(DH));
-    attn_kernel<DH, G><<<dim3(a.Hkv, a.rows), kAttnThreads, smem, st>>>(a, scale, lcap);
-    FSB_LAUNCH_CHECK();
+    FSB_LAUNCH((attn_kernel<DH, G>), dim3(a.Hkv, a.rows), dim3(kAttnThreads), smem, st, a, scale, lcap);
     return 0;
 }
 
@@ -541,8 +591,7 @@ int launch_attn(const AttnArgs& a, cudaStream_t st) {
 
 int launch_swiglu(const SwigluArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
-    swiglu_kernel<<<dim3(cdiv(a.I, 256), a.rows), 256, 0, st>>>(a);
-    FSB_LAUNCH_CHECK();
+    FSB_LAUNCH(swiglu_kernel, dim3(cdiv(a.I, 256), a.rows), dim3(256), 0, st, a);
     return 0;
 }
 
@@ -550,24 +599,20 @@ int launch_sample(const SampleArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
     FSB_CHECK(a.n > 0 && a.n <= kSampleMaxN, "sample: n=%d out of range", a.n);
     FSB_CHECK(a.top_k >= 1, "sample: top_k must be >= 1");
-    sample_kernel<<<a.rows, kSampleThreads, 0, st>>>(a);
-    FSB_LAUNCH_CHECK();
+    FSB_LAUNCH(sample_kernel, dim3(a.rows), dim3(kSampleThreads), 0, st, a);
     return 0;
 }
 
 int launch_frame_end(const FrameEndArgs& a, cudaStream_t st) {
-    frame_end_kernel<<<a.rows, 32, 0, st>>>(a);
-    FSB_LAUNCH_CHECK();
-    step_inc_kernel<<<1, 1, 0, st>>>(a.step);
-    FSB_LAUNCH_CHECK();
+    FSB_LAUNCH(frame_end_kernel, dim3(a.rows), dim3(32), 0, st, a);
+    FSB_LAUNCH(step_inc_kernel, dim3(1), dim3(1), 0, st, a.step);
     return 0;
 }
 
 int launch_gather_rows(const __nv_bfloat16* src, const int* idx, __nv_bfloat16* dst, int rows, int D,
                        cudaStream_t st) {
     if (rows <= 0) return 0;
-    gather_rows_kernel<<<rows, 256, 0, st>>>(src, idx, dst, D);
-    FSB_LAUNCH_CHECK();
+    FSB_LAUNCH(gather_rows_kernel, dim3(rows), dim3(256), 0, st, src, idx, dst, D);
     return 0;
 }
 

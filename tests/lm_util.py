@@ -88,3 +88,44 @@ def assert_tokens_match(got: torch.Tensor, ref: torch.Tensor, traces: list, cfg:
         return f - T
     assert got.shape == ref.shape, f"{what}: length {got.shape} vs {ref.shape}"
     return n - T
+
+
+def teacher_forced_check(model, cfg: O.LMConfig, w: dict, prompt: torch.Tensor, n: int, what: str = ""):
+    """Frame-by-frame parity with the ORACLE's history fed back (so one near-tie cannot hide the rest of
+    the run). For every frame the CUDA engine decodes one frame from the oracle's previous frame; its
+    token id / codes are compared row by row. A mismatch is tolerated only where the oracle's own
+    decision was a bf16 near-tie (top-2 gap <= 2 ulp); the rest of that frame (which then sees a
+    different code history) is skipped. Returns (frames_fully_equal, near_ties)."""
+    from fish_speech_b200.models.text2semantic.inference import decode_one_token_ar
+
+    T = prompt.shape[1]
+    traces = []
+    ref = O.generate(O.setup(cfg, w), prompt, n, temperature=0.7, top_p=0.7, top_k=1, traces=traces,
+                     stop_on_im_end=False, noise=False)
+    temp, top_p = torch.tensor(0.7), torch.tensor(0.7)
+    C1 = cfg.num_codebooks + 1
+    prev = torch.zeros((C1, 10), dtype=torch.int32)
+    equal, ties = 0, 0
+    for f in range(n):
+        if f == 0:
+            x, pos, pt = prompt.view(1, C1, -1).cuda(), torch.arange(T).cuda(), None
+        else:
+            x = ref[:, T + f - 1].view(1, C1, 1).cuda()
+            pos, pt = torch.tensor([T + f - 1]).cuda(), prev.cuda()
+        tok = decode_one_token_ar(model, x, pos, temp, top_p, 1, None, None, None, previous_tokens=pt).cpu().view(-1)
+        want = ref[:, T + f].to(torch.int32)
+        if torch.equal(tok.to(torch.int32), want):
+            equal += 1
+        else:
+            r = int((tok.to(torch.int32) != want).nonzero()[0])
+            tr = traces[f]
+            logits = restricted(cfg, tr["slow_logits"]) if r <= 1 else tr["fast_logits"][r - 2]
+            top2 = torch.topk(logits.float(), 2).values
+            gap, ulp = float(top2[0] - top2[1]), float(top2[0].abs()) * 2 ** -7
+            assert gap <= 2 * ulp, (f"{what}: frame {f} row {r}: got {tok.tolist()} want {want.tolist()} "
+                                   f"(oracle top-2 gap {gap:.4g} > 2 ulp = {2 * ulp:.4g})")
+            ties += 1
+        if f > 0:
+            prev = prev.roll(-1, dims=1)
+            prev[:, -1] = want
+    return equal, ties

@@ -12,7 +12,8 @@ import pytest
 import torch
 
 from oracle import lm_oracle as O
-from tests.lm_util import assert_tokens_match, build_model, load_golden, make_prompt, restricted
+from tests.lm_util import (assert_tokens_match, build_model, load_golden, make_prompt, restricted,
+                            teacher_forced_check)
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).parent / "golden"
@@ -94,12 +95,10 @@ def test_batch_invariance_and_ragged_prompts():
                           top_p=0.7, top_k=1)
     solo = build_model(cfg, w, max_batch=1)
     for i, p in enumerate(prompts):
-        st = O.setup(cfg, w)
-        traces = []
-        ref = O.generate(st, p, n, temperature=0.7, top_p=0.7, top_k=1, traces=traces, noise=False)
         one = _gen(solo, p, n, temperature=0.7, top_p=0.7, top_k=1)
         assert torch.equal(outs[i].cpu().to(torch.int32), one.to(torch.int32)), f"seq {i}: batch != solo"
-        assert assert_tokens_match(one, ref, traces, cfg, p.shape[1], f"seq {i}") >= n - 1
+        eq, ties = teacher_forced_check(solo, cfg, w, p, n, f"seq {i}")
+        assert eq >= n - 3, f"seq {i}: only {eq}/{n} frames identical ({ties} near-ties)"
 
 
 def test_prefill_chunking_equals_single_pass():
@@ -123,11 +122,9 @@ def test_s2pro_layer_geometry_greedy():
                      semantic_end_id=8095, im_end_id=3999)
     w = O.make_weights(cfg, seed=51, head_gain=6.0)
     p = make_prompt(cfg, 51, 24)
-    st = O.setup(cfg, w)
-    traces = []
-    ref = O.generate(st, p, 5, temperature=0.7, top_p=0.7, top_k=1, traces=traces, noise=False)
-    got = _gen(build_model(cfg, w), p, 5, temperature=0.7, top_p=0.7, top_k=1)
-    assert assert_tokens_match(got, ref, traces, cfg, 24, "s2pro geometry") >= 3
+    eq, ties = teacher_forced_check(build_model(cfg, w), cfg, w, p, 6, "s2pro geometry")
+    # 10 x 4096-way decisions per frame on random weights: a few bf16 near-ties are expected
+    assert eq >= 3, f"only {eq}/6 frames identical ({ties} near-ties)"
 
 
 def test_stop_on_im_end_and_max_len_errors():
