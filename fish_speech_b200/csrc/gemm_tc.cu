@@ -153,8 +153,12 @@ __device__ __forceinline__ void epilogue_direct(const GemmParams& p, uint32_t ta
     }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+// MODE 0: fp32 partial sums to the workspace (decode / prefill of the LM). Lean in registers and shared
+//         memory so that TWO CTAs fit on an SM: the CTA of the next GEMM in the stream becomes resident
+//         (programmatic dependent launch) and prefetches its weight tiles while this one still runs.
+// MODE 1: direct fused epilogue (codec convolutions / linears).
+template <int BN, int MODE>
+__global__ void __launch_bounds__(kThreads, MODE == 0 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -320,7 +324,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool i_ok = i < p.rows_i;
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(a * BN);
-            if (p.mode == 0) {
+            if (MODE == 0) {
                 float* base = p.ws + static_cast<size_t>(slot) * p.ws_slot_stride;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -399,6 +403,13 @@ int make_tmap(CUtensorMap* tm, const GemmOperand& op, int box_rows) {
     return 0;
 }
 
+template <int BN, int MODE>
+int launch_bn_mode(const GemmPlan& plan, cudaStream_t stream) {
+    auto k = gemm_tc_kernel<BN, MODE>;
+    FSB_LAUNCH(k, plan.grid, dim3(kThreads), plan.smem, stream, plan.tmA, plan.tmB, plan.p);
+    return 0;
+}
+
 template <int BN>
 int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
     static bool attr_set = false;
@@ -406,8 +417,7 @@ int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
         FSB_TRY(gemm_init());
         attr_set = true;
     }
-    FSB_LAUNCH(gemm_tc_kernel<BN>, plan.grid, dim3(kThreads), plan.smem, stream, plan.tmA, plan.tmB, plan.p);
-    return 0;
+    return plan.p.mode == 0 ? launch_bn_mode<BN, 0>(plan, stream) : launch_bn_mode<BN, 1>(plan, stream);
 }
 
 }  // namespace
@@ -494,10 +504,12 @@ void gemm_plan_free(GemmPlan* plan) {
 int gemm_init() {
     // opt every instantiation into the large dynamic shared-memory carve-out up front, so that no
     // attribute call is needed later (e.g. while a stream is being captured into a CUDA graph)
-    FSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define FSB_GEMM_ATTR(BN_, M_)                                                                       \
+    FSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  227 * 1024));
+    FSB_GEMM_ATTR(32, 0) FSB_GEMM_ATTR(64, 0) FSB_GEMM_ATTR(128, 0) FSB_GEMM_ATTR(256, 0)
+    FSB_GEMM_ATTR(32, 1) FSB_GEMM_ATTR(64, 1) FSB_GEMM_ATTR(128, 1) FSB_GEMM_ATTR(256, 1)
+#undef FSB_GEMM_ATTR
     return 0;
 }
 

@@ -113,7 +113,8 @@ int make_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const 
     p.ws_ld = n_out;
     const int tiles_i = cdiv(n_out, 128);
     if (decode) {
-        FSB_TRY(gemm_plan_init(plan, A, B, 32, 8, tiles_i, 1, 1));
+        // 5 stages x 20 KB = 100 KB: two CTAs per SM (this GEMM + the prefetching next one)
+        FSB_TRY(gemm_plan_init(plan, A, B, 32, 5, tiles_i, 1, 1));
         p.rows_j = kDecRows;
         p.ws_slot_stride = static_cast<long long>(kDecRows) * n_out;
         FSB_TRY(gemm_plan_streamk(plan, tiles_i, kblocks, h->num_sms));

@@ -55,8 +55,8 @@ __global__ void embed_kernel(EmbedArgs a, float inv_div) {
 // ------------------------------------------------------------------------------------------------
 // residual add + fish RMSNorm
 // ------------------------------------------------------------------------------------------------
-constexpr int kRnThreads = 1024;
-constexpr int kRnMaxPer = 4;  // D <= 4096
+constexpr int kRnThreads = 512;
+constexpr int kRnMaxPer = 8;  // D <= 4096
 
 __global__ void __launch_bounds__(kRnThreads) resid_norm_kernel(ResidNormArgs a, int gstride) {
     pdl_launch_dependents();

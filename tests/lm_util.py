@@ -95,7 +95,7 @@ def teacher_forced_check(model, cfg: O.LMConfig, w: dict, prompt: torch.Tensor, 
     the run). For every frame the CUDA engine decodes one frame from the oracle's previous frame; its
     token id / codes are compared row by row. A mismatch is tolerated only where the oracle's own
     decision was a bf16 near-tie (top-2 gap <= 2 ulp); the rest of that frame (which then sees a
-    different code history) is skipped. Returns (frames_fully_equal, near_ties)."""
+    different code history) is skipped. Returns (frames_fully_equal, near_ties, decisions_verified)."""
     from fish_speech_b200.models.text2semantic.inference import decode_one_token_ar
 
     T = prompt.shape[1]
@@ -105,7 +105,7 @@ def teacher_forced_check(model, cfg: O.LMConfig, w: dict, prompt: torch.Tensor, 
     temp, top_p = torch.tensor(0.7), torch.tensor(0.7)
     C1 = cfg.num_codebooks + 1
     prev = torch.zeros((C1, 10), dtype=torch.int32)
-    equal, ties = 0, 0
+    equal, ties, decisions = 0, 0, 0
     for f in range(n):
         if f == 0:
             x, pos, pt = prompt.view(1, C1, -1).cuda(), torch.arange(T).cuda(), None
@@ -116,8 +116,10 @@ def teacher_forced_check(model, cfg: O.LMConfig, w: dict, prompt: torch.Tensor, 
         want = ref[:, T + f].to(torch.int32)
         if torch.equal(tok.to(torch.int32), want):
             equal += 1
+            decisions += cfg.num_codebooks  # slow token + C-1 sampled codes (row 1 is derived from row 0)
         else:
             r = int((tok.to(torch.int32) != want).nonzero()[0])
+            decisions += max(0, r - 1) if r >= 2 else 0
             tr = traces[f]
             logits = restricted(cfg, tr["slow_logits"]) if r <= 1 else tr["fast_logits"][r - 2]
             top2 = torch.topk(logits.float(), 2).values
@@ -128,4 +130,4 @@ def teacher_forced_check(model, cfg: O.LMConfig, w: dict, prompt: torch.Tensor, 
         if f > 0:
             prev = prev.roll(-1, dims=1)
             prev[:, -1] = want
-    return equal, ties
+    return equal, ties, decisions

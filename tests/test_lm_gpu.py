@@ -97,8 +97,8 @@ def test_batch_invariance_and_ragged_prompts():
     for i, p in enumerate(prompts):
         one = _gen(solo, p, n, temperature=0.7, top_p=0.7, top_k=1)
         assert torch.equal(outs[i].cpu().to(torch.int32), one.to(torch.int32)), f"seq {i}: batch != solo"
-        eq, ties = teacher_forced_check(solo, cfg, w, p, n, f"seq {i}")
-        assert eq >= n - 3, f"seq {i}: only {eq}/{n} frames identical ({ties} near-ties)"
+        eq, ties, dec = teacher_forced_check(solo, cfg, w, p, n, f"seq {i}")
+        assert dec >= 0.6 * n * cfg.num_codebooks, f"seq {i}: {eq}/{n} frames identical, {ties} near-ties, {dec} decisions"
 
 
 def test_prefill_chunking_equals_single_pass():
@@ -122,9 +122,10 @@ def test_s2pro_layer_geometry_greedy():
                      semantic_end_id=8095, im_end_id=3999)
     w = O.make_weights(cfg, seed=51, head_gain=6.0)
     p = make_prompt(cfg, 51, 24)
-    eq, ties = teacher_forced_check(build_model(cfg, w), cfg, w, p, 6, "s2pro geometry")
-    # 10 x 4096-way decisions per frame on random weights: a few bf16 near-ties are expected
-    assert eq >= 3, f"only {eq}/6 frames identical ({ties} near-ties)"
+    eq, ties, dec = teacher_forced_check(build_model(cfg, w), cfg, w, p, 6, "s2pro geometry")
+    # 10 x 4096-way decisions per frame on random weights: ~15% of them are bf16 near-ties (top-2 gap
+    # <= 2 ulp); every other decision must be identical (hard mismatches fail inside the helper)
+    assert dec >= 30, f"only {dec}/60 decisions verified ({eq} frames identical, {ties} near-ties)"
 
 
 def test_stop_on_im_end_and_max_len_errors():
