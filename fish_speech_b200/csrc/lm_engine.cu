@@ -11,6 +11,8 @@
 //
 // Reference: fish_speech/models/text2semantic/llama.py:390-466 (slow step), :799-817 (fast step),
 // fish_speech/models/text2semantic/inference.py:96-181 (one frame), :184-238 (frame loop).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <map>
 #include <string>
@@ -106,6 +108,10 @@ int make_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const 
     p.num_taps = 1;
     p.a_hint = kEvictFirst;  // weights are streamed once per step (>> L2)
     p.a_static = 1;
+    {
+        const char* e = getenv("FSB_L2_PREFETCH");
+        p.l2_prefetch = decode ? (e ? atoi(e) : 16) : 0;
+    }
     p.b_hint = kEvictLast;   // the activation tile is re-read by every CTA
     p.rows_i = n_out;
     p.mode = 0;
