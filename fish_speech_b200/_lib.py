@@ -78,6 +78,20 @@ def lib() -> C.CDLL:
     L.fsb_lm_reset.argtypes = [vp, vp]
     L.fsb_lm_buffer.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.fsb_lm_bench_gemms.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(i32), vp]
+    f32p, i32p, ll = C.c_void_p, C.POINTER(C.c_int), C.c_longlong
+    L.fsb_conv_gemm.argtypes = [vp, i32, i32, i32, i32, ll, vp, i32, i32, i32, i32p, i32, vp, vp, vp, i32, vp, vp, vp,
+                                vp, i32, vp]
+    L.fsb_linear_f32.argtypes = [vp, i32, i32, vp, i32, vp, vp]
+    L.fsb_codebook_sum.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    L.fsb_dwconv_ln.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_float, vp, vp]
+    L.fsb_final_conv_tanh.argtypes = [vp, vp, C.c_float, i32, i32, i32, i32, vp, vp]
+    L.fsb_first_conv.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
+    L.fsb_snake.argtypes = [vp, vp, vp, ll, i32, vp, vp]
+    L.fsb_vq_encode.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
+    L.fsb_resid_scale_norm.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
+    L.fsb_qkv_rope.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]
+    L.fsb_window_attn.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    L.fsb_swiglu_f32.argtypes = [vp, i32, i32, vp, vp]
     L.fsb_op_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
     _lib = L
     return L

@@ -179,14 +179,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // Work items of this CTA: a stream-K range (several segments, each of one output tile) or the
-    // single tile named by blockIdx.
+    // Work items of this CTA: a stream-K range (several segments, each of one output tile), a range of
+    // the persistent tiled schedule, or the single tile named by blockIdx.
     int item_begin = 0, item_end = 1;
     if (p.sched != nullptr) {
         item_begin = p.cta_items[blockIdx.x];
         item_end = p.cta_items[blockIdx.x + 1];
+    } else if (p.tiled_total > 0) {
+        item_begin = static_cast<int>(static_cast<long long>(p.tiled_total) * blockIdx.x / gridDim.x);
+        item_end = static_cast<int>(static_cast<long long>(p.tiled_total) * (blockIdx.x + 1) / gridDim.x);
     }
-    const int z = blockIdx.z;
+    int z = blockIdx.z;
     auto get_item = [&](int n, int& i0, int& j0, int& kb0, int& kb1, int& slot) {
         if (p.sched != nullptr) {
             const int4 w = p.sched[n];
@@ -195,6 +198,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             kb0 = w.y;
             kb1 = w.z;
             slot = w.w;
+        } else if (p.tiled_total > 0) {
+            const int per_z = p.tiled_ti * p.tiled_tj;
+            z = n / per_z;
+            const int rem = n - z * per_z;
+            const int ti = rem / p.tiled_tj;
+            i0 = ti * kBlockM;
+            j0 = (rem - ti * p.tiled_tj) * BN;
+            kb0 = 0;
+            kb1 = p.kb_per_tap * p.num_taps;
+            slot = 0;
         } else {
             i0 = blockIdx.x * kBlockM;
             j0 = blockIdx.y * BN;
@@ -502,6 +515,20 @@ int gemm_plan_streamk(GemmPlan* plan, int tiles_i, int kblocks, int num_ctas) {
     plan->p.sched = reinterpret_cast<const int4*>(plan->sched_dev);
     plan->p.cta_items = plan->cta_items_dev;
     plan->grid = dim3(static_cast<unsigned>(num_ctas), 1, 1);
+    return 0;
+}
+
+int gemm_plan_tiled(GemmPlan* plan, int tiles_i, int tiles_j, int batch) {
+    const long long total = static_cast<long long>(tiles_i) * tiles_j * batch;
+    FSB_CHECK(total > 0 && total < (1ll << 31), "gemm_plan_tiled: bad tile count");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long ctas = total < sms ? total : sms;  // one persistent CTA per SM (smem-limited)
+    plan->p.tiled_total = static_cast<int>(total);
+    plan->p.tiled_ti = tiles_i;
+    plan->p.tiled_tj = tiles_j;
+    plan->grid = dim3(static_cast<unsigned>(ctas), 1, 1);
     return 0;
 }
 

@@ -34,6 +34,7 @@ struct GemmParams {
     // ---- work decomposition ----
     const int4* sched;     // optional items {tile_i | tile_j<<16, kb_begin, kb_end, slot}; else blockIdx
     const int* cta_items;  // [grid.x + 1] item range of each CTA (stream-K)
+    int tiled_total, tiled_ti, tiled_tj;  // persistent tiled mode: items = (z, tile_i, tile_j), tile_j fastest
     int rows_i, rows_j;  // valid output extents
     // ---- epilogue: mode 0 = fp32 partials ws[slot][j][i]; mode 1 = direct ----
     int mode;
@@ -82,6 +83,8 @@ int gemm_plan_init(GemmPlan* plan, const GemmOperand& A, const GemmOperand& B, i
 // k-blocks each, spread evenly over `num_ctas` CTAs. Partials of tile t land in slots
 // [0, nparts[t]) of the workspace.
 int gemm_plan_streamk(GemmPlan* plan, int tiles_i, int kblocks, int num_ctas);
+// Persistent tiled schedule (no table): tiles_i x tiles_j x batch full-K tiles spread over <= 2 CTAs per SM.
+int gemm_plan_tiled(GemmPlan* plan, int tiles_i, int tiles_j, int batch);
 void gemm_plan_free(GemmPlan* plan);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 int gemm_init();  // set kernel attributes (idempotent)

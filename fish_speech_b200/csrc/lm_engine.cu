@@ -110,7 +110,7 @@ int make_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const 
     p.a_static = 1;
     {
         const char* e = getenv("FSB_L2_PREFETCH");
-        p.l2_prefetch = decode ? (e ? atoi(e) : 16) : 0;
+        p.l2_prefetch = decode ? (e ? atoi(e) : 0) : 0;
     }
     p.b_hint = kEvictLast;   // the activation tile is re-read by every CTA
     p.rows_i = n_out;

@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(kRnThreads) resid_norm_kernel(ResidNormArgs a,
             if (a.parts.ws) {
                 float y = sum_parts(a.parts, row, d);
                 if (a.bias) y += bf2f(a.bias[d]);
-                x = rbf(x + rbf(y));
+                y = rbf(y);
+                if (a.scale) y *= bf2f(a.scale[d]);
+                x = rbf(x + y);
             }
             v[e] = x;
             ss += x * x;

@@ -32,6 +32,7 @@ int launch_embed(const EmbedArgs& a, cudaStream_t st);
 struct ResidNormArgs {
     Partials parts;
     const __nv_bfloat16* bias;  // [D] or null (attention_o_bias)
+    const __nv_bfloat16* scale;  // [D] or null: y *= scale (codec LayerScale, modded_dac.py:329-341)
     const __nv_bfloat16* x_in;  // [rows, D] residual input (null => 0)
     __nv_bfloat16* x_out;       // [rows, D] (may alias x_in; null => don't store)
     const __nv_bfloat16* norm_w;  // [D] (null => no norm output)

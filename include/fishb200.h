@@ -135,6 +135,55 @@ int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* l
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Codec ("Firefly VQ-GAN" = modified Descript-DAC) operators
+ *   replace DAC.from_indices / DAC.encode and everything under them
+ *     (fish_speech/models/dac/modded_dac.py:874-946, fish_speech/models/dac/rvq.py:293-366).
+ * Activations are channels-last bf16 [B][T][C]. The host mirror (fish_speech_b200/models/dac/) walks the
+ * reference's module tree and issues one call per layer; weight-norm is folded once at load.
+ * ---------------------------------------------------------------------------------------------- */
+/* Conv1d / ConvTranspose1d / Linear as a tcgen05 multi-tap implicit-im2col GEMM with fused epilogue:
+ *   out[b][t][co] = epi( sum_tap sum_ci x[b][t + shifts[tap]][ci] * w[co][tap*kpad + ci] )
+ * rows outside [0, T_in) read as zero (= CausalConvNet's left pad, modded_dac.py:546-552).
+ * epi: +bias[co]; GELU if act==1; *gamma[co]; +resid[b][t][co]; tanh if act==2; out0 = value,
+ * out1 = Snake(value; alpha[co]) (dac.nn.layers.Snake1d) for the consuming layer. */
+int fsb_conv_gemm(const void* d_x, int B, int T_in, int C_in, int row_stride, long long batch_stride,
+                  const void* d_w, int C_out, int taps, int kpad, const int* shifts, int T_out,
+                  const float* d_bias, const float* d_gamma, const void* d_resid, int act,
+                  void* d_out0, void* d_out1, const float* d_alpha, const float* d_inv_alpha, int out_f32,
+                  void* stream);
+/* ws[row][n] (fp32) = sum_k x[row][k] * w[n][k] — feeds the transformer glue below. */
+int fsb_linear_f32(const void* d_x, int rows, int K, const void* d_w, int N, float* d_ws, void* stream);
+/* z[b][t][:] = tab_0[idx[b][0][t]] + sum_{c>=1} tab_c[idx[b][c][t]]  (rvq.py:352-363; tab_c =
+ * out_proj_c(codebook_c), fp32 [size_c][D]); indices are clamped to the table size like the reference. */
+int fsb_codebook_sum(const int32_t* d_idx, const float* const* d_tabs, const int32_t* d_sizes, int ncb, int B,
+                     int T, int D, void* d_out, void* stream);
+/* ConvNeXt front: causal depthwise conv (k taps) + LayerNorm (rvq.py:176-179). w fp32 [C][K]. */
+int fsb_dwconv_ln(const void* d_x, const float* d_w, const float* d_bias, const float* d_ln_w, const float* d_ln_b,
+                  int B, int T, int C, int K, float eps, void* d_y, void* stream);
+/* Decoder tail: conv K taps C->1 on the Snake'd activation + tanh -> fp32 waveform (modded_dac.py:793-797). */
+int fsb_final_conv_tanh(const void* d_a, const float* d_w, float bias, int B, int T, int C, int K, float* d_wav,
+                        void* stream);
+/* Encoder head: conv K taps 1->C on the fp32 waveform (modded_dac.py:683); raw and/or Snake'd output. */
+int fsb_first_conv(const float* d_wav, const float* d_w, const float* d_bias, const float* d_alpha,
+                   const float* d_inv_alpha, int B, int T, int C, int K, void* d_raw, void* d_act, void* stream);
+int fsb_snake(const void* d_x, const float* d_alpha, const float* d_inv_alpha, long long n, int C, void* d_y,
+              void* stream);
+/* 1 semantic + n residual vector-quantiser stages per latent frame (rvq.py:304-317, dac VectorQuantize). */
+int fsb_vq_encode(const void* d_z, const float* d_in_w, const float* d_in_b, const float* d_cbn,
+                  const int32_t* d_cb_off, const int32_t* d_sizes, const float* const* d_tabs, int S, int cd, int B,
+                  int T, int D, int32_t* d_codes, void* stream);
+/* WindowLimitedTransformer glue (modded_dac.py:174-346) on fp32 GEMM results. */
+int fsb_resid_scale_norm(const float* d_y, int ld, const void* d_scale, const void* d_x_in, void* d_x_out,
+                         const void* d_norm_w, void* d_n_out, int rows, int D, float eps, int round_bf16,
+                         void* stream);
+int fsb_qkv_rope(const float* d_qkv, int rows, int H, int Hkv, int Dh, const void* d_freqs, const int32_t* d_row_seq,
+                 const int32_t* d_row_pos, void* d_q, void* d_k, void* d_v, int S, void* stream);
+int fsb_window_attn(const void* d_q, const void* d_k, const void* d_v, const int32_t* d_row_seq,
+                    const int32_t* d_row_pos, int rows, int H, int Hkv, int Dh, int S, int window, void* d_out,
+                    void* stream);
+int fsb_swiglu_f32(const float* d_y, int rows, int I, void* d_h, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Unit-test hooks (used by tests/ only)
  * ---------------------------------------------------------------------------------------------- */
 /* out[j][i] (fp32, ld = m) = sum_k A[i][k] * B[j][k]; A [m,k], B [n,k] bf16 row-major.

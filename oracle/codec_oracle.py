@@ -123,9 +123,9 @@ def make_weights(cfg: CodecConfig, seed: int = 1234, dtype=torch.float32) -> dic
 
     def res_unit(prefix, c):
         snake(f"{prefix}.block.0", c)
-        conv(f"{prefix}.block.1.conv", c, c, 7, gain=0.7)
+        conv(f"{prefix}.block.1.conv", c, c, 7, gain=0.5)
         snake(f"{prefix}.block.2", c)
-        conv(f"{prefix}.block.3.conv", c, c, 1, gain=0.7)
+        conv(f"{prefix}.block.3.conv", c, c, 1, gain=0.5)
 
     def tfm(prefix, t: TfmConfig):
         for l in range(t.n_layer):
@@ -201,7 +201,7 @@ def make_weights(cfg: CodecConfig, seed: int = 1234, dtype=torch.float32) -> dic
             res_unit(f"{p}.{2 + j}", cout)
     n = len(cfg.decoder_rates) + 1
     snake(f"decoder.model.{n}", cout)
-    conv(f"decoder.model.{n + 1}.conv", 1, cout, 7, gain=0.5)
+    conv(f"decoder.model.{n + 1}.conv", 1, cout, 7, gain=0.12)
     return w
 
 
