@@ -43,43 +43,31 @@ def s2pro_cfg():
     return s2pro_args(max_seq_len=512)
 
 
-def gpu_weights(cfg, device, seed=1234):
-    """Seeded synthetic bf16 weights generated directly on the device (no checkpoint, no network)."""
-    g = torch.Generator(device=device).manual_seed(seed)
-    std = cfg.initializer_range
-
-    def lin(o, i, gain=1.0):
-        return (torch.randn(o, i, generator=g, device=device, dtype=torch.float32) * (std * gain)).to(torch.bfloat16)
-
-    def nrm(n):
-        return (1.0 + 0.1 * torch.randn(n, generator=g, device=device)).to(torch.bfloat16)
-
-    w = {"embeddings.weight": lin(cfg.vocab_size, cfg.dim, 4.0),
-         "codebook_embeddings.weight": lin(cfg.codebook_size * cfg.num_codebooks, cfg.dim)}
-
-    def block(prefix, dim, nh, nkv, hd, inter, qk):
-        w[f"{prefix}.attention.wqkv.weight"] = lin((nh + 2 * nkv) * hd, dim)
-        w[f"{prefix}.attention.wo.weight"] = lin(dim, nh * hd)
-        if qk:
-            w[f"{prefix}.attention.q_norm.weight"] = nrm(hd)
-            w[f"{prefix}.attention.k_norm.weight"] = nrm(hd)
-        w[f"{prefix}.feed_forward.w1.weight"] = lin(inter, dim)
-        w[f"{prefix}.feed_forward.w3.weight"] = lin(inter, dim)
-        w[f"{prefix}.feed_forward.w2.weight"] = lin(dim, inter)
-        w[f"{prefix}.ffn_norm.weight"] = nrm(dim)
-        w[f"{prefix}.attention_norm.weight"] = nrm(dim)
-
-    for l in range(cfg.n_layer):
-        block(f"layers.{l}", cfg.dim, cfg.n_head, cfg.n_local_heads, cfg.head_dim, cfg.intermediate_size,
-              cfg.attention_qk_norm)
-    w["norm.weight"] = nrm(cfg.dim)
-    w["fast_embeddings.weight"] = lin(cfg.codebook_size, cfg.fast_dim)
-    for l in range(cfg.n_fast_layer):
-        block(f"fast_layers.{l}", cfg.fast_dim, cfg.fast_n_head, cfg.fast_n_local_heads, cfg.fast_head_dim,
-              cfg.fast_intermediate_size, cfg.fast_attention_qk_norm)
-    w["fast_norm.weight"] = nrm(cfg.fast_dim)
-    w["fast_output.weight"] = lin(cfg.codebook_size, cfg.fast_dim, 4.0)
-    return w
+def codec_decode_macs(c, T: int) -> float:
+    """Multiply-accumulates of DAC.from_indices for one utterance of T frames (every conv / linear /
+    attention product; SURVEY §8: 866.9 GMAC at T=256 for the full geometry)."""
+    D = c.latent_dim
+    t = c.quant_tfm
+    macs = 0.0
+    per_tok = t.n_layer * (3 * t.dim * t.n_head * t.head_dim + t.dim * t.n_head * t.head_dim + 3 * t.dim * t.intermediate_size)
+    win = t.window_size or T
+    attn = t.n_layer * 2 * t.n_head * t.head_dim * sum(min(i + 1, win) for i in range(T))
+    macs += per_tok * T + attn
+    Tc = T
+    for f in reversed(c.downsample_factor):
+        macs += Tc * D * D * f  # transposed conv k = stride = f
+        Tc *= f
+        macs += Tc * (7 * D + 2 * 4 * D * D)  # ConvNeXt: depthwise k7 + two pointwise
+    macs += Tc * 7 * D * c.decoder_dim
+    cin = c.decoder_dim
+    for s_ in c.decoder_rates:
+        cout = cin // 2
+        macs += Tc * cin * cout * 2 * s_  # transposed conv k = 2*stride: 2 taps per output phase, s phases
+        Tc *= s_
+        macs += 3 * Tc * (7 * cout * cout + cout * cout)
+        cin = cout
+    macs += Tc * 7 * cin
+    return macs
 
 
 def make_prompts(cfg, n, first_seed):
@@ -197,13 +185,15 @@ def main():
     ap.add_argument("--frames", type=int, default=N_FRAMES)
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-codec", action="store_true", help="time the LM stages only")
     ap.add_argument("--profile-only", action="store_true", help="run the timed step once and exit (for ncu)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    workload = f"batch-{args.batch} text->codec, {T_PROMPT}-token prompts, {args.frames} codec frames/utt, S2-Pro 4B geometry"
+    workload = (f"batch-{args.batch} text->codec->wav, {T_PROMPT}-token prompts, {args.frames} codec frames/utt, "
+                "S2-Pro 4B Dual-AR + 391M DAC codec geometry")
 
     if args.impl == "reference":
         if rank != 0:
@@ -223,7 +213,10 @@ def main():
 
     from fish_speech_b200 import _lib
     from fish_speech_b200.models.text2semantic.inference import generate_batch
+    from fish_speech_b200 import synthetic
     from fish_speech_b200.configs import S2PRO_IM_END_ID
+    from fish_speech_b200.models.dac.inference import load_codec_config
+    from fish_speech_b200.models.dac.modded_dac import DAC
     from fish_speech_b200.models.text2semantic.llama import DualARTransformer
 
     torch.cuda.set_device(local_rank)
@@ -232,22 +225,34 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg = s2pro_cfg()
     B, NF = args.batch, args.frames
-    weights = gpu_weights(cfg, dev)
+    weights = synthetic.lm_state_dict(cfg, dev)
     model = DualARTransformer(cfg, weights, device=dev, im_end_id=S2PRO_IM_END_ID)
     model.max_rows = B * T_PROMPT
     model.setup_caches(max_batch_size=B, max_seq_len=cfg.max_seq_len)
     del weights
     eng = model.engine
+    ccfg = load_codec_config("modded_dac_vq")
+    with torch.cuda.device(dev):
+        cw = synthetic.codec_state_dict(ccfg, dev)
+        dac = DAC(ccfg, cw, device=dev)
+        del cw
+    stages = ["lm_prefill", "lm_decode"] + ([] if args.no_codec else ["codec_decode"])
     # utterance shard of this rank: utts[rank::world] of 32*world prompts (seeds 42..)
     prompts_host = [p.pin_memory() for p in make_prompts(cfg, B * world, 42)[rank::world]]
     prompts_dev = [p.to(dev) for p in prompts_host]
     sp = eng.sampling(0.7, 0.7, 1, 42)
     L = _lib.lib()
 
+    def codec_stage():
+        codes = eng.buffer("out_tokens")[:B, 1:, :NF].contiguous()
+        return dac.from_indices(codes)
+
     def step_resident():
         eng.reset()
         eng.prefill(prompts_dev, list(range(B)), sp, do_sample=True)
         eng.decode(B, NF - 1, sp, use_graph=True)
+        if not args.no_codec:
+            codec_stage()
 
     def barrier():
         torch.cuda.synchronize()
@@ -291,13 +296,23 @@ def main():
     def step_e2e():
         outs = generate_batch(model=model, prompts=[p.to(dev, non_blocking=True) for p in prompts_host],
                               max_new_tokens=NF, temperature=0.7, top_p=0.7, top_k=1, seed=42)
-        return [o[:, T_PROMPT:].cpu() for o in outs]
+        if args.no_codec:
+            return [o[:, T_PROMPT:].cpu() for o in outs]
+        # fixed-length workload (<|im_end|> cannot win with these weights): one padded codec batch
+        codes = torch.stack([o[1:, T_PROMPT:T_PROMPT + NF] for o in outs]).contiguous()
+        return dac.from_indices(codes).cpu()
 
     step_e2e()
     ms_e2e = timed(step_e2e, max(1, args.steps // 2)) / max(1, args.steps // 2)
     e2e_value = audio_s / (ms_e2e / 1e3)
     h2d = sum(p.numel() * p.element_size() for p in prompts_host) * world
-    d2h = B * world * (cfg.num_codebooks + 1) * NF * 4
+    d2h = B * world * (cfg.num_codebooks + 1) * NF * 4 if args.no_codec else B * world * NF * FRAME * 4
+    codec = None
+    if not args.no_codec:
+        codec_stage()
+        codec_ms = timed(codec_stage, 3) / 3
+        flops = 2.0 * codec_decode_macs(ccfg, NF) * B
+        codec = {"ms": codec_ms, "tflops": flops / (codec_ms / 1e3) / 1e12, "flop_per_step": flops}
 
     # ---- roofline of the dominant kernel: the decode GEMM stream, measured live ----
     import ctypes as C
@@ -322,7 +337,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": workload, "stages": ["lm_prefill", "lm_decode"], "utterances": B * world,
+                "workload": workload, "stages": stages, "utterances": B * world,
                 "frames_per_s": B * world * NF / (ms_per_step / 1e3),
                 "codec_tokens_per_s": B * world * NF * cfg.num_codebooks / (ms_per_step / 1e3),
                 "ms_per_frame": frame_ms, "sampling": "greedy top_k=1 T=0.7 top_p=0.7",
@@ -342,6 +357,12 @@ def main():
             },
             "clocks": clk,
         }
+        if codec is not None:
+            pkv = pk.get("bf16_tflops_sustained", 1400.0)
+            out["roofline_codec"] = {"bound": "tensor", "achieved": codec["tflops"], "peak": pkv, "unit": "TFLOP/s",
+                                     "frac": codec["tflops"] / pkv, "traffic": None, "ms_per_step": codec["ms"],
+                                     "kernel": "gemm_tc_kernel<BN,1> implicit-im2col conv GEMMs (tcgen05) + glue",
+                                     "flop_per_step": codec["flop_per_step"]}
     if world > 1:
         dist.barrier()
     if rank == 0:

@@ -114,7 +114,7 @@ class DAC:
         self._keep: list[torch.Tensor] = []
         self._bufs: dict = {}
         self._rope: dict = {}
-        self._sd = {k: v.detach().float() for k, v in state_dict.items()}
+        self._sd = {k: v.detach().float() for k, v in state_dict.items()}  # folded on the device they live on
         with torch.cuda.device(self._device):
             self._pack()
         del self._sd
@@ -155,7 +155,7 @@ class DAC:
         c_out, c_in, k = w.shape
         if stride == 1:
             kpad = _pad64(c_in)
-            m = torch.zeros(c_out, k, kpad)
+            m = torch.zeros(c_out, k, kpad, device=w.device)
             m[:, :, :c_in] = w.permute(0, 2, 1)
             shifts = [-(k - 1 - j) * dilation for j in range(k)]
             taps, c_in_eff = k, c_in
@@ -164,7 +164,7 @@ class DAC:
             taps = k // stride
             c_in_eff = stride * c_in
             kpad = _pad64(c_in_eff)
-            m = torch.zeros(c_out, taps, kpad)
+            m = torch.zeros(c_out, taps, kpad, device=w.device)
             # tap q covers kernel positions j = q*stride + r, r < stride, laid out (r, ci)
             wr = w.permute(0, 2, 1).reshape(c_out, taps, stride * c_in)
             m[:, :, :c_in_eff] = wr
@@ -183,7 +183,7 @@ class DAC:
         assert k % stride == 0
         taps = k // stride
         kpad = _pad64(c_in)
-        m = torch.zeros(stride * c_out, taps, kpad)
+        m = torch.zeros(stride * c_out, taps, kpad, device=w.device)
         for q in range(taps):
             # rows (p, co)  <-  W[ci, co, p + q*stride]
             blk = w[:, :, q * stride:(q + 1) * stride]  # [ci, co, p]
@@ -197,7 +197,7 @@ class DAC:
         w = self._sd[f"{prefix}.weight"]
         n, k = w.shape
         kpad = _pad64(k)
-        m = torch.zeros(n, kpad)
+        m = torch.zeros(n, kpad, device=w.device)
         m[:, :k] = w
         bias = self._sd.get(f"{prefix}.bias") if with_bias else None
         return _Conv(self._dev(m, torch.bfloat16), self._dev(bias, torch.float32) if bias is not None else None,
