@@ -226,6 +226,9 @@ def main():
     cfg = s2pro_cfg()
     B, NF = args.batch, args.frames
     weights = synthetic.lm_state_dict(cfg, dev)
+    # fixed-length workload ("<|im_end|> bias set to -inf"): a zero head row gives
+    # <|im_end|> the logit 0, which never beats the best of 4096 random semantic logits
+    weights["embeddings.weight"][S2PRO_IM_END_ID] = 0
     model = DualARTransformer(cfg, weights, device=dev, im_end_id=S2PRO_IM_END_ID)
     model.max_rows = B * T_PROMPT
     model.setup_caches(max_batch_size=B, max_seq_len=cfg.max_seq_len)
