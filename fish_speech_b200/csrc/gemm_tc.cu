@@ -178,6 +178,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long* trace =
+        p.trace ? p.trace + (static_cast<size_t>(p.trace_id) * gridDim.x + blockIdx.x) * 3 : nullptr;
+    if (trace && threadIdx.x == 0) trace[0] = globaltimer_ns();
 
     // Work items of this CTA: a stream-K range (several segments, each of one output tile), a range of
     // the persistent tiled schedule, or the single tile named by blockIdx.
@@ -283,6 +286,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             pdl_wait();
+            if (trace) trace[1] = globaltimer_ns();
             waited = true;
             (void)waited;
             for (int n = item_begin; n < item_end; ++n) {
@@ -377,6 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (trace && threadIdx.x == 0) trace[2] = globaltimer_ns();
     if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);

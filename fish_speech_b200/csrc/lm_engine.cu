@@ -624,6 +624,25 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int
     return 0;
 }
 
+int fsb_lm_trace_gemms(fsb_lm* h, unsigned long long* d_trace, int max_launches, int* grid_out, void* stream) {
+    // One slow layer's four GEMMs repeated, each CTA recording globaltimer at start / after the
+    // programmatic-dependency wait / at exit: shows whether consecutive kernels really overlap.
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Stack& s = h->slow;
+    int id = 0;
+    for (int l = 0; l < s.nl && id + 4 <= max_launches; ++l) {
+        GemmPlan* plans[4] = {&s.dec[l].qkv, &s.dec[l].wo, &s.dec[l].w13, &s.dec[l].w2};
+        for (int k = 0; k < 4; ++k) {
+            GemmPlan q = *plans[k];
+            q.p.trace = d_trace;
+            q.p.trace_id = id++;
+            FSB_TRY(gemm_launch(q, st));
+        }
+    }
+    if (grid_out) *grid_out = static_cast<int>(s.dec[0].qkv.grid.x);
+    return id;
+}
+
 int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* launches_per_rep, void* stream) {
     // Every weight-streaming GEMM of one decode frame (36 slow layers x 4, head, 10 fast passes x
     // (4 layers x 4 + head)) back to back, without the glue kernels: the measured stream of the

@@ -134,6 +134,10 @@ int fsb_lm_buffer(fsb_lm* h, const char* name, void** d_ptr, size_t* bytes);
 int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* launches_per_rep,
                        void* stream);
 
+/* Diagnostic: GEMM chain with per-CTA globaltimer stamps {start, after dependency wait, end}; returns the
+ * number of launches traced (negative on error is not used: 0 launches means failure). */
+int fsb_lm_trace_gemms(fsb_lm* h, unsigned long long* d_trace, int max_launches, int* grid_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Codec ("Firefly VQ-GAN" = modified Descript-DAC) operators
  *   replace DAC.from_indices / DAC.encode and everything under them
