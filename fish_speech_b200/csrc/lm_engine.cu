@@ -119,11 +119,15 @@ int make_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const 
     p.ws_ld = n_out;
     const int tiles_i = cdiv(n_out, 128);
     if (decode) {
-        // 5 stages x 20 KB = 100 KB: two CTAs per SM (this GEMM + the prefetching next one)
-        FSB_TRY(gemm_plan_init(plan, A, B, 32, 5, tiles_i, 1, 1));
+        // ring depth / CTAs per SM are tunable for experiments (FSB_STAGES, FSB_CTAS_PER_SM)
+        const char* es = getenv("FSB_STAGES");
+        const char* ec = getenv("FSB_CTAS_PER_SM");
+        const int stages = es ? atoi(es) : 5;
+        const int per_sm = ec ? atoi(ec) : 1;
+        FSB_TRY(gemm_plan_init(plan, A, B, 32, stages, tiles_i, 1, 1));
         p.rows_j = kDecRows;
         p.ws_slot_stride = static_cast<long long>(kDecRows) * n_out;
-        FSB_TRY(gemm_plan_streamk(plan, tiles_i, kblocks, h->num_sms));
+        FSB_TRY(gemm_plan_streamk(plan, tiles_i, kblocks, h->num_sms * per_sm));
         FSB_CHECK(static_cast<size_t>(plan->max_parts) * kDecRows * n_out <= h->ws_floats,
                   "partial workspace too small");
     } else {
@@ -422,7 +426,7 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     const int Nmax = std::max({Nqkv_s, Nqkv_f, 2 * s.I, 2 * f.I, s.D, f.D, h->head_rows, cfg->codebook_size});
     const int R = std::max(cfg->max_rows, 128);
     // partial workspace: decode needs max_parts(<=8) x 32 x N ; prefill needs rows x N
-    h->ws_floats = std::max<size_t>(static_cast<size_t>(8) * kDecRows * Nmax, static_cast<size_t>(R) * Nmax);
+    h->ws_floats = std::max<size_t>(static_cast<size_t>(24) * kDecRows * Nmax, static_cast<size_t>(R) * Nmax);
 #define TRYC(x)                  \
     do {                         \
         if ((x) != 0) {          \
