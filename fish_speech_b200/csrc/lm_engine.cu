@@ -122,8 +122,8 @@ int make_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const 
         // ring depth / CTAs per SM are tunable for experiments (FSB_STAGES, FSB_CTAS_PER_SM)
         const char* es = getenv("FSB_STAGES");
         const char* ec = getenv("FSB_CTAS_PER_SM");
-        const int stages = es ? atoi(es) : 5;
-        const int per_sm = ec ? atoi(ec) : 1;
+        const int stages = es ? atoi(es) : 4;   // measured best on B200: 4 stages x 2 CTAs per SM
+        const int per_sm = ec ? atoi(ec) : 2;
         FSB_TRY(gemm_plan_init(plan, A, B, 32, stages, tiles_i, 1, 1));
         p.rows_j = kDecRows;
         p.ws_slot_stride = static_cast<long long>(kDecRows) * n_out;
