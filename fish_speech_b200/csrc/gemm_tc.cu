@@ -17,7 +17,6 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom row
-constexpr int kThreads = 192;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;
 
 // UMMA shared-memory descriptor for a K-major, 128B-swizzled tile whose rows are 128 B apart and
@@ -41,114 +40,96 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
 }
 
-// Direct epilogue for one accumulator: bias -> GELU -> gamma -> +residual -> tanh -> store raw (out0)
-// and/or snake-activated (out1) in bf16 (or fp32).
+// Direct epilogue for one 32-column chunk of an accumulator row:
+//   bias -> GELU -> gamma -> +residual -> tanh -> store raw (out0) and/or Snake-activated (out1).
+// Fast path (channels on the columns, bf16 outputs contiguous along the columns, full chunk): per-column
+// parameters come in as float4 broadcast loads, 8 columns are processed at a time to keep the register
+// footprint small, sin() is the MUFU approximation (arguments are O(10), outputs are bf16).
+__device__ __forceinline__ float snake_fast(float v, float a, float ia) {
+    const float s = __sinf(a * v);
+    return fmaf(ia * s, s, v);
+}
+
 template <int BN>
-__device__ __forceinline__ void epilogue_direct(const GemmParams& p, uint32_t taddr, int i, bool i_ok,
-                                                int j0, int z) {
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* r, int i, int jbase, int z) {
     const size_t zoff = static_cast<size_t>(z) * p.o_zs;
-    const bool vec = (p.o_js == 1) && !p.out_f32 && ((p.o_is & 7) == 0) && ((p.o_zs & 7) == 0);
-    float bi = 0.f, gi = 1.f, sa = 0.f, sia = 0.f;
-    if (p.chan_on_i && i_ok) {
-        if (p.bias) bi = p.bias[i];
-        if (p.gamma) gi = p.gamma[i];
-        if (p.out1) {
-            sa = p.snake_alpha[i];
-            sia = p.snake_inv_alpha[i];
+    const size_t rowoff = zoff + static_cast<size_t>(i) * p.o_is;
+    const bool fast = !p.chan_on_i && (p.o_js == 1) && !p.out_f32 && ((p.o_is & 7) == 0) && ((p.o_zs & 7) == 0) &&
+                      (jbase + 32 <= p.rows_j);
+    if (fast) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = jbase + q * 8;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[q * 8 + e]);
+            if (p.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + j));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + j + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (p.act == ACT_GELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+            }
+            if (p.gamma) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + j));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + j + 4));
+                v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+                v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+            }
+            if (p.resid) {
+                const uint4 u = *reinterpret_cast<const uint4*>(p.resid + rowoff + j);
+                v[0] += bf_lo(u.x); v[1] += bf_hi(u.x); v[2] += bf_lo(u.y); v[3] += bf_hi(u.y);
+                v[4] += bf_lo(u.z); v[5] += bf_hi(u.z); v[6] += bf_lo(u.w); v[7] += bf_hi(u.w);
+            }
+            if (p.act == ACT_TANH) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = tanhf(v[e]);
+            }
+            if (p.out0) {
+                uint4 u;
+                u.x = pack_bf2(v[0], v[1]); u.y = pack_bf2(v[2], v[3]);
+                u.z = pack_bf2(v[4], v[5]); u.w = pack_bf2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out0) + rowoff + j) = u;
+            }
+            if (p.out1) {
+                const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.snake_alpha + j));
+                const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.snake_alpha + j + 4));
+                const float4 i0 = __ldg(reinterpret_cast<const float4*>(p.snake_inv_alpha + j));
+                const float4 i1 = __ldg(reinterpret_cast<const float4*>(p.snake_inv_alpha + j + 4));
+                uint4 u;
+                u.x = pack_bf2(snake_fast(v[0], a0.x, i0.x), snake_fast(v[1], a0.y, i0.y));
+                u.y = pack_bf2(snake_fast(v[2], a0.z, i0.z), snake_fast(v[3], a0.w, i0.w));
+                u.z = pack_bf2(snake_fast(v[4], a1.x, i1.x), snake_fast(v[5], a1.y, i1.y));
+                u.w = pack_bf2(snake_fast(v[6], a1.z, i1.z), snake_fast(v[7], a1.w, i1.w));
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out1) + rowoff + j) = u;
+            }
         }
+        return;
     }
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        tmem_ld_wait();
-        if (!i_ok) continue;
-        const int jbase = j0 + c0;
-        if (jbase >= p.rows_j) continue;
-        const size_t rowoff = zoff + static_cast<size_t>(i) * p.o_is;
-        float v[32], w[32];
+    // generic path (ragged chunks, fp32 outputs, channels on the lanes)
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-            const int j = jbase + jj;
-            float x = __uint_as_float(r[jj]);
-            float b = bi, g = gi, a = sa, ia = sia;
-            if (!p.chan_on_i && j < p.rows_j) {
-                if (p.bias) b = p.bias[j];
-                if (p.gamma) g = p.gamma[j];
-                if (p.out1) {
-                    a = p.snake_alpha[j];
-                    ia = p.snake_inv_alpha[j];
-                }
-            }
-            x += b;
-            if (p.act == ACT_GELU) x = gelu_erf(x);
-            x *= g;
-            v[jj] = x;
-            w[jj] = a;  // stash alpha / inv_alpha for the snake pass
-            r[jj] = __float_as_uint(ia);
-        }
-        const bool full32 = (jbase + 32 <= p.rows_j);
-        if (p.resid) {
-            if (vec && full32) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.resid + rowoff + jbase);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint4 u = rp[q];
-                    v[q * 8 + 0] += bf_lo(u.x); v[q * 8 + 1] += bf_hi(u.x);
-                    v[q * 8 + 2] += bf_lo(u.y); v[q * 8 + 3] += bf_hi(u.y);
-                    v[q * 8 + 4] += bf_lo(u.z); v[q * 8 + 5] += bf_hi(u.z);
-                    v[q * 8 + 6] += bf_lo(u.w); v[q * 8 + 7] += bf_hi(u.w);
-                }
-            } else {
-#pragma unroll
-                for (int jj = 0; jj < 32; ++jj) {
-                    const int j = jbase + jj;
-                    if (j < p.rows_j)
-                        v[jj] += bf2f(p.resid[rowoff + static_cast<size_t>(j) * p.o_js]);
-                }
-            }
-        }
-        if (p.act == ACT_TANH) {
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) v[jj] = tanhf(v[jj]);
+    for (int jj = 0; jj < 32; ++jj) {
+        const int j = jbase + jj;
+        if (j >= p.rows_j) continue;
+        const int c = p.chan_on_i ? i : j;
+        float x = __uint_as_float(r[jj]);
+        if (p.bias) x += p.bias[c];
+        if (p.act == ACT_GELU) x = gelu_erf(x);
+        if (p.gamma) x *= p.gamma[c];
+        const size_t idx = rowoff + static_cast<size_t>(j) * p.o_js;
+        if (p.resid) x += bf2f(p.resid[idx]);
+        if (p.act == ACT_TANH) x = tanhf(x);
+        if (p.out0) {
+            if (p.out_f32) reinterpret_cast<float*>(p.out0)[idx] = x;
+            else reinterpret_cast<__nv_bfloat16*>(p.out0)[idx] = f2bf(x);
         }
         if (p.out1) {
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-                const float s = sinf(w[jj] * v[jj]);
-                w[jj] = v[jj] + __uint_as_float(r[jj]) * s * s;
-            }
-        }
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-            void* outp = o == 0 ? p.out0 : p.out1;
-            if (outp == nullptr) continue;
-            const float* src = o == 0 ? v : w;
-            if (vec && full32) {
-                uint4* op =
-                    reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(outp) + rowoff + jbase);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 u;
-                    u.x = pack_bf2(src[q * 8 + 0], src[q * 8 + 1]);
-                    u.y = pack_bf2(src[q * 8 + 2], src[q * 8 + 3]);
-                    u.z = pack_bf2(src[q * 8 + 4], src[q * 8 + 5]);
-                    u.w = pack_bf2(src[q * 8 + 6], src[q * 8 + 7]);
-                    op[q] = u;
-                }
-            } else {
-#pragma unroll
-                for (int jj = 0; jj < 32; ++jj) {
-                    const int j = jbase + jj;
-                    if (j < p.rows_j) {
-                        const size_t idx = rowoff + static_cast<size_t>(j) * p.o_js;
-                        if (p.out_f32)
-                            reinterpret_cast<float*>(outp)[idx] = src[jj];
-                        else
-                            reinterpret_cast<__nv_bfloat16*>(outp)[idx] = f2bf(src[jj]);
-                    }
-                }
-            }
+            const float y = snake_fast(x, p.snake_alpha[c], p.snake_inv_alpha[c]);
+            if (p.out_f32) reinterpret_cast<float*>(p.out1)[idx] = y;
+            else reinterpret_cast<__nv_bfloat16*>(p.out1)[idx] = f2bf(y);
         }
     }
 }
@@ -157,14 +138,22 @@ __device__ __forceinline__ void epilogue_direct(const GemmParams& p, uint32_t ta
 //         memory so that TWO CTAs fit on an SM: the CTA of the next GEMM in the stream becomes resident
 //         (programmatic dependent launch) and prefetches its weight tiles while this one still runs.
 // MODE 1: direct fused epilogue (codec convolutions / linears).
+template <int MODE>
+struct GemmRoles {
+    static constexpr int kEpiWarps = MODE == 0 ? 4 : 8;  // MODE 1: two warps per TMEM lane quadrant
+    static constexpr int kThreads = (kEpiWarps + 2) * 32;
+};
+
 template <int BN, int MODE>
-__global__ void __launch_bounds__(kThreads, MODE == 0 ? 2 : 1)
+__global__ void __launch_bounds__(GemmRoles<MODE>::kThreads, MODE == 0 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int kBTileBytes = BN * kBlockK * 2;
     constexpr int kStageBytes = kATileBytes + kBTileBytes;
     constexpr int kTmemCols = 2 * BN;  // two accumulators: epilogue of item n overlaps MMA of n+1
+    constexpr int kEpiWarps = GemmRoles<MODE>::kEpiWarps;
+    constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
@@ -220,7 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     };
 
-    if (warp == 4 && lane == 0) {
+    if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < stages; ++s) {
@@ -229,18 +218,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull0 + 8u * a, 1);
-            mbar_init(tempty0 + 8u * a, 4);  // one arrival per epilogue warp
+            mbar_init(tempty0 + 8u * a, kEpiWarps);  // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     pdl_launch_dependents();  // let the consumer kernel get resident; it blocks in griddepcontrol.wait
-    if (warp == 4) {
+    if (warp == kProducerWarp) {
         // ===== TMA producer: the ring keeps flowing across item boundaries =====
         // Operand A (weights when a_static) does not depend on the upstream kernel: its tiles for the
         // whole ring are requested BEFORE griddepcontrol.wait, so the HBM stream of this GEMM starts
@@ -309,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kMmaWarp) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BN);
@@ -350,10 +339,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t aph = static_cast<uint32_t>((n - item_begin) >> 1) & 1u;
             mbar_wait(tfull0 + 8u * a, aph);
             tc_fence_after();
-            const int i = i0 + warp * 32 + lane;
+            const int quad = warp & 3, half = warp >> 2;  // TMEM lane quadrant is fixed by warp id % 4
+            const int i = i0 + quad * 32 + lane;
             const bool i_ok = i < p.rows_i;
             const uint32_t taddr =
-                tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(a * BN);
+                tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(a * BN);
             if (MODE == 0) {
                 float* base = p.ws + static_cast<size_t>(slot) * p.ws_slot_stride;
 #pragma unroll 1
@@ -371,7 +361,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             } else {
-                epilogue_direct<BN>(p, taddr, i, i_ok, j0, z);
+                // the two warps of a lane quadrant take alternate 32-column chunks
+#pragma unroll 1
+                for (int c0 = half * 32; c0 < BN; c0 += 32 * (kEpiWarps / 4)) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (i_ok && j0 + c0 < p.rows_j) epilogue_chunk<BN>(p, r, i, j0 + c0, z);
+                }
             }
             // release the accumulator to the MMA warp
             tc_fence_before();
@@ -382,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (trace && threadIdx.x == 0) trace[2] = globaltimer_ns();
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
@@ -437,7 +434,7 @@ int make_tmap(CUtensorMap* tm, const GemmOperand& op, int box_rows) {
 template <int BN, int MODE>
 int launch_bn_mode(const GemmPlan& plan, cudaStream_t stream) {
     auto k = gemm_tc_kernel<BN, MODE>;
-    FSB_LAUNCH(k, plan.grid, dim3(kThreads), plan.smem, stream, plan.tmA, plan.tmB, plan.p);
+    FSB_LAUNCH(k, plan.grid, dim3(GemmRoles<MODE>::kThreads), plan.smem, stream, plan.tmA, plan.tmB, plan.p);
     return 0;
 }
 
