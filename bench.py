@@ -117,6 +117,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_gemm32_ncu_full.json); None if no capture is committed."""
+    try:
+        d = json.loads((ROOT / "profiles" / "r01_gemm32_ncu_full.json").read_text())
+        return d["avg_dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         return json.loads((ROOT / "MEASURED_PEAKS.json").read_text()), "measured"
@@ -353,7 +363,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "hbm", "achieved": gemm_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": gemm_gbs / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                "frac": gemm_gbs / pk["hbm_gbs"], "traffic": ncu_traffic(), "peak_kind": pk_kind,
                 "kernel": "gemm_tc_kernel<32> (tcgen05 + TMA weight streaming, stream-K)",
                 "bytes_per_launch": wb.value / nl.value, "launches": nl.value * reps,
                 "avg_launch_us": gemm_ms * 1e3 / (nl.value * reps),
