@@ -21,6 +21,7 @@
 #include "../../include/fishb200.h"
 #include "gemm_tc.cuh"
 #include "lm_kernels.cuh"
+#include "lm_persist.cuh"
 
 using namespace fsb;
 
@@ -43,6 +44,8 @@ struct Stack {
     std::vector<LayerW> w;
     std::vector<LayerPlans> dec;  // BN=32, stream-K, B operand = decode workspaces
     std::vector<LayerPlans> pf;   // BN=128 tiles, B operand = prefill workspaces (slow only)
+    std::vector<LayerPlans> pk;   // stream-K over one CTA per SM, for the persistent stack kernel
+    PkLayer* pk_layers = nullptr;  // device array
     bf16 *kcache = nullptr, *vcache = nullptr;
     const bf16* freqs = nullptr;
     size_t cache_layer_stride = 0;
@@ -73,6 +76,9 @@ struct fsb_lm {
     // debug
     float *slow_logits = nullptr, *fast_logits = nullptr;
     bf16* dbg_x = nullptr;
+    bool persistent = false;
+    int pk_stages = 8;
+    unsigned* pk_bar = nullptr;
     // decode graph cache
     cudaGraphExec_t graph_exec = nullptr;
     int graph_batch = -1;
@@ -98,7 +104,7 @@ int dalloc(fsb_lm* h, T** p, size_t count, const char* name = nullptr) {
 
 // Decode-orientation plan: A = weight [n_out, k] on the TMEM lanes, B = activations [rows, k].
 int make_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const bf16* act, int act_rows,
-              bool decode) {
+              bool decode, int force_per_sm = 0) {
     memset(plan, 0, sizeof(*plan));
     GemmOperand A{w, k, n_out, 1, k, static_cast<long long>(n_out) * k};
     GemmOperand B{act, k, act_rows, 1, k, static_cast<long long>(act_rows) * k};
@@ -123,7 +129,7 @@ int make_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const 
         const char* es = getenv("FSB_STAGES");
         const char* ec = getenv("FSB_CTAS_PER_SM");
         const int stages = es ? atoi(es) : 4;   // measured best on B200: 4 stages x 2 CTAs per SM
-        const int per_sm = ec ? atoi(ec) : 2;
+        const int per_sm = force_per_sm ? force_per_sm : (ec ? atoi(ec) : 2);
         FSB_TRY(gemm_plan_init(plan, A, B, 32, stages, tiles_i, 1, 1));
         p.rows_j = kDecRows;
         p.ws_slot_stride = static_cast<long long>(kDecRows) * n_out;
@@ -173,6 +179,24 @@ struct RowCtx {
 int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool stop_after_kv,
               bf16* dbg, cudaStream_t st) {
     const float eps = h->cfg.norm_eps;
+    if (h->persistent && c.decode && s.pk_layers != nullptr) {
+        PkArgs A{};
+        A.layers = s.pk_layers;
+        A.nl = s.nl; A.rows = c.rows; A.D = s.D; A.H = s.H; A.Hkv = s.Hkv; A.Dh = s.Dh; A.I = s.I; A.S = s.S;
+        A.eps = eps;
+        A.bf16_math = s.bf16_math;
+        A.qk_norm = s.qk_norm ? 1 : 0;
+        A.kv_only_last = stop_after_kv ? 1 : 0;
+        A.stages = h->pk_stages;
+        A.row_seq = c.row_seq;
+        A.row_pos = c.row_pos;
+        A.freqs = s.freqs;
+        A.xres = c.xres; A.xn = c.xn; A.attn = c.attn; A.hbuf = c.hbuf;
+        A.ws = h->ws;
+        A.bar = h->pk_bar;
+        (void)final_norm;  // baked into the last layer's next_norm
+        return launch_stack_persistent(A, h->num_sms, st);
+    }
     for (int l = 0; l < s.nl; ++l) {
         const LayerW& w = s.w[l];
         LayerPlans& P = c.decode ? s.dec[l] : s.pf[l];
@@ -500,6 +524,56 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     };
     TRYC(build(s, true));
     TRYC(build(f, false));
+    {
+        const char* ep = getenv("FSB_PERSISTENT");
+        h->persistent = ep && ep[0] == '1';
+        const char* es = getenv("FSB_PK_STAGES");
+        if (es) h->pk_stages = atoi(es);
+    }
+    if (h->persistent) {
+        TRYC(pk_init());
+        TRYC(dalloc(h, &h->pk_bar, 2));
+        auto build_pk = [&](Stack& st, const bf16* final_norm) -> int {
+            st.pk.resize(st.nl);
+            std::vector<PkLayer> host(st.nl);
+            const int Nqkv = (st.H + 2 * st.Hkv) * st.Dh;
+            auto fill = [&](PkGemm& g, GemmPlan& p) {
+                g.tmA = p.tmA;
+                g.tmB = p.tmB;
+                g.sched = reinterpret_cast<const int4*>(p.sched_dev);
+                g.cta_items = p.cta_items_dev;
+                g.nparts = p.nparts_dev;
+                g.n_out = p.p.ws_ld;
+                g.slot_stride = p.p.ws_slot_stride;
+            };
+            for (int l = 0; l < st.nl; ++l) {
+                const LayerW& lw = st.w[l];
+                FSB_TRY(make_plan(h, &st.pk[l].qkv, lw.wqkv, Nqkv, st.D, h->xn_d, kDecRows, true, 1));
+                FSB_TRY(make_plan(h, &st.pk[l].wo, lw.wo, st.D, st.H * st.Dh, h->attn_d, kDecRows, true, 1));
+                FSB_TRY(make_plan(h, &st.pk[l].w13, lw.w13, 2 * st.I, st.D, h->xn_d, kDecRows, true, 1));
+                FSB_TRY(make_plan(h, &st.pk[l].w2, lw.w2, st.D, st.I, h->h_d, kDecRows, true, 1));
+                PkLayer& L = host[l];
+                memset(&L, 0, sizeof(L));
+                fill(L.qkv, st.pk[l].qkv);
+                fill(L.wo, st.pk[l].wo);
+                fill(L.w13, st.pk[l].w13);
+                fill(L.w2, st.pk[l].w2);
+                L.bqkv = lw.bqkv;
+                L.q_norm = st.qk_norm ? lw.q_norm : nullptr;
+                L.k_norm = st.qk_norm ? lw.k_norm : nullptr;
+                L.bo = lw.bo;
+                L.ffn_norm = lw.ffn_norm;
+                L.next_norm = (l + 1 < st.nl) ? st.w[l + 1].attn_norm : final_norm;
+                L.kcache = st.kcache + l * st.cache_layer_stride;
+                L.vcache = st.vcache + l * st.cache_layer_stride;
+            }
+            FSB_TRY(dalloc(h, &st.pk_layers, static_cast<size_t>(st.nl)));
+            FSB_CUDA(cudaMemcpy(st.pk_layers, host.data(), host.size() * sizeof(PkLayer), cudaMemcpyHostToDevice));
+            return 0;
+        };
+        TRYC(build_pk(s, h->norm_w));
+        TRYC(build_pk(f, h->fast_norm_w));
+    }
     TRYC(make_plan(h, &h->head_plan, h->head_w, h->head_rows, s.D, h->xn_d, kDecRows, true));
     TRYC(make_plan(h, &h->fast_out_plan, h->fast_out_w, cfg->codebook_size, f.D, h->xn_d, kDecRows, true));
     if (h->has_proj) TRYC(make_plan(h, &h->proj_plan, h->fast_proj_w, f.D, s.D, h->xn_d, kDecRows, true));
@@ -515,6 +589,7 @@ void fsb_lm_destroy(fsb_lm* h) {
     auto free_plans = [](Stack& st) {
         for (auto& p : st.dec) { gemm_plan_free(&p.qkv); gemm_plan_free(&p.wo); gemm_plan_free(&p.w13); gemm_plan_free(&p.w2); }
         for (auto& p : st.pf) { gemm_plan_free(&p.qkv); gemm_plan_free(&p.wo); gemm_plan_free(&p.w13); gemm_plan_free(&p.w2); }
+        for (auto& p : st.pk) { gemm_plan_free(&p.qkv); gemm_plan_free(&p.wo); gemm_plan_free(&p.w13); gemm_plan_free(&p.w2); }
     };
     free_plans(h->slow);
     free_plans(h->fast);

@@ -6,26 +6,6 @@ namespace fsb {
 
 namespace {
 
-// Sum of the stream-K partials of one output element, always in slot order (deterministic and
-// independent of the batch). Loads are issued four at a time so the L2 latencies overlap.
-__device__ __forceinline__ float sum_parts(const Partials& P, int j, int i) {
-    const int np = P.nparts ? __ldg(P.nparts + (i >> 7)) : 1;
-    const float* p = P.ws + static_cast<size_t>(j) * P.ld + i;
-    const size_t ss = static_cast<size_t>(P.slot_stride);
-    float s = 0.f;
-    for (int q = 0; q < np; q += 4) {
-        const float a0 = p[static_cast<size_t>(q) * ss];
-        const float a1 = q + 1 < np ? p[static_cast<size_t>(q + 1) * ss] : 0.f;
-        const float a2 = q + 2 < np ? p[static_cast<size_t>(q + 2) * ss] : 0.f;
-        const float a3 = q + 3 < np ? p[static_cast<size_t>(q + 3) * ss] : 0.f;
-        s += a0;
-        s += a1;
-        s += a2;
-        s += a3;
-    }
-    return s;
-}
-
 // ------------------------------------------------------------------------------------------------
 // embed: llama.py:399-420
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,40 @@
+// Persistent per-stack decode kernel (lm_persist.cu): device-side descriptors.
+#pragma once
+#include "common.cuh"
+
+namespace fsb {
+
+struct PkGemm {            // one weight-streaming GEMM inside the persistent kernel
+    CUtensorMap tmA, tmB;  // weights [n_out, K] (box 128 rows), activations [32, K] (box 32 rows)
+    const int4* sched;     // stream-K items {tile, kb_begin, kb_end, slot}
+    const int* cta_items;  // [grid + 1]
+    const int* nparts;     // partial count per 128-feature tile
+    int n_out;
+    int pad;
+    long long slot_stride;
+};
+
+struct PkLayer {
+    PkGemm qkv, wo, w13, w2;
+    const __nv_bfloat16 *bqkv, *q_norm, *k_norm, *bo, *ffn_norm, *next_norm;
+    __nv_bfloat16 *kcache, *vcache;
+};
+
+struct PkArgs {
+    const PkLayer* layers;
+    int nl, rows, D, H, Hkv, Dh, I, S;
+    float eps;
+    int bf16_math, qk_norm, kv_only_last, stages;
+    const int* row_seq;
+    const int* row_pos;
+    const __nv_bfloat16* freqs;
+    __nv_bfloat16 *xres, *xn, *attn, *hbuf;
+    float* ws;
+    unsigned* bar;  // [2]: phase counter, exit counter
+};
+
+int pk_init();
+size_t pk_scratch_bytes(int H, int Hkv, int Dh, int S);
+int launch_stack_persistent(const PkArgs& A, int grid, cudaStream_t st);
+
+}  // namespace fsb
