@@ -456,13 +456,13 @@ int gemm_plan_init(GemmPlan* plan, const GemmOperand& A, const GemmOperand& B, i
     return 0;
 }
 
-int gemm_plan_streamk(GemmPlan* plan, int tiles_i, int kblocks, int num_ctas) {
+int gemm_plan_streamk(GemmPlan* plan, int tiles_i, int kblocks, int num_ctas, bool keep_empty_ctas) {
     // Units are (tile, k-block) pairs in tile-major order; CTA c streams units [c*U/n, (c+1)*U/n).
     // Where that range crosses a tile boundary it becomes several items (one per tile touched); the
     // CTA runs them back to back with the TMA ring never draining, so every SM pulls the same number
     // of weight bytes. Partials of tile t land in workspace slots [0, nparts[t]).
     const long long U = static_cast<long long>(tiles_i) * kblocks;
-    if (num_ctas > U) num_ctas = static_cast<int>(U);
+    if (num_ctas > U && !keep_empty_ctas) num_ctas = static_cast<int>(U);
     std::vector<int4> items;
     std::vector<int> cta_items(num_ctas + 1, 0);
     std::vector<int> nparts(tiles_i, 0);

@@ -84,7 +84,7 @@ int gemm_plan_init(GemmPlan* plan, const GemmOperand& A, const GemmOperand& B, i
 // Host-scheduled stream-K for the skinny (decode) case: `tiles_i` x 1 output tiles, `kblocks`
 // k-blocks each, spread evenly over `num_ctas` CTAs. Partials of tile t land in slots
 // [0, nparts[t]) of the workspace.
-int gemm_plan_streamk(GemmPlan* plan, int tiles_i, int kblocks, int num_ctas);
+int gemm_plan_streamk(GemmPlan* plan, int tiles_i, int kblocks, int num_ctas, bool keep_empty_ctas = false);
 // Persistent tiled schedule (no table): tiles_i x tiles_j x batch full-K tiles spread over <= 2 CTAs per SM.
 int gemm_plan_tiled(GemmPlan* plan, int tiles_i, int tiles_j, int batch);
 void gemm_plan_free(GemmPlan* plan);

@@ -133,7 +133,8 @@ int make_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const 
         FSB_TRY(gemm_plan_init(plan, A, B, 32, stages, tiles_i, 1, 1));
         p.rows_j = kDecRows;
         p.ws_slot_stride = static_cast<long long>(kDecRows) * n_out;
-        FSB_TRY(gemm_plan_streamk(plan, tiles_i, kblocks, h->num_sms * per_sm));
+        // the persistent kernel indexes the schedule by blockIdx.x of a full grid: keep empty CTA ranges
+        FSB_TRY(gemm_plan_streamk(plan, tiles_i, kblocks, h->num_sms * per_sm, force_per_sm != 0));
         FSB_CHECK(static_cast<size_t>(plan->max_parts) * kDecRows * n_out <= h->ws_floats,
                   "partial workspace too small");
     } else {
