@@ -489,6 +489,10 @@ __global__ void __launch_bounds__(kPkThreads, 1) stack_kernel(const __grid_const
         }
     } else {
         // ===== workers (warps 0-7); warps 0-3 also run the GEMM epilogues =====
+        // The barrier counter is shared with the previous launch (which resets it on exit): under
+        // programmatic dependent launch this CTA may be resident before that launch has finished, so the
+        // thread that touches the counter first waits for the upstream grids.
+        if (threadIdx.x == 0) pdl_wait();
         int acc_it = 0;
         unsigned bidx = 0;
         for (int l = 0; l < A.nl; ++l) {
