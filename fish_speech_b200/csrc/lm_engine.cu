@@ -79,6 +79,7 @@ struct fsb_lm {
     bool persistent = false;
     int pk_stages = 8;
     unsigned* pk_bar = nullptr;
+    unsigned long long* pk_trace = nullptr;
     // decode graph cache
     cudaGraphExec_t graph_exec = nullptr;
     int graph_batch = -1;
@@ -195,6 +196,8 @@ int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool
         A.xres = c.xres; A.xn = c.xn; A.attn = c.attn; A.hbuf = c.hbuf;
         A.ws = h->ws;
         A.bar = h->pk_bar;
+        A.trace = (s.bf16_math == 0) ? h->pk_trace : nullptr;  // slow stack only
+        A.trace_max = 1024;
         (void)final_norm;  // baked into the last layer's next_norm
         return launch_stack_persistent(A, h->num_sms, st);
     }
@@ -534,6 +537,7 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     if (h->persistent) {
         TRYC(pk_init());
         TRYC(dalloc(h, &h->pk_bar, 2));
+        if (getenv("FSB_PK_TRACE")) TRYC(dalloc(h, &h->pk_trace, 1024, "pk_trace"));
         auto build_pk = [&](Stack& st, const bf16* final_norm) -> int {
             st.pk.resize(st.nl);
             std::vector<PkLayer> host(st.nl);

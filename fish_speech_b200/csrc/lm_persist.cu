@@ -495,6 +495,12 @@ __global__ void __launch_bounds__(kPkThreads, 1) stack_kernel(const __grid_const
         if (threadIdx.x == 0) pdl_wait();
         int acc_it = 0;
         unsigned bidx = 0;
+        int tix = 0;
+        auto stamp = [&]() {
+            if (A.trace && blockIdx.x == 0 && threadIdx.x == 0 && tix < A.trace_max) A.trace[tix] = globaltimer_ns();
+            ++tix;
+        };
+        stamp();
         for (int l = 0; l < A.nl; ++l) {
             const PkLayer& L = A.layers[l];
             const bool last = l == A.nl - 1;
@@ -502,7 +508,9 @@ __global__ void __launch_bounds__(kPkThreads, 1) stack_kernel(const __grid_const
             for (int g = 0; g < ng; ++g) {
                 const PkGemm& G2 = g == 0 ? L.qkv : (g == 1 ? L.wo : (g == 2 ? L.w13 : L.w2));
                 if (warp < 4) epilogue_gemm(G2, R, acc_it, tmem_base, A.ws, A.rows);
+                stamp();
                 grid_barrier(A.bar, ++bidx * grid);
+                stamp();
                 if (g == 0) {
                     phase_prep_attn<DH, G>(A, L, scratch, last && A.kv_only_last);
                 } else if (g == 1) {
@@ -512,7 +520,9 @@ __global__ void __launch_bounds__(kPkThreads, 1) stack_kernel(const __grid_const
                 } else {
                     phase_resid_norm(A, L.w2, nullptr, L.next_norm, scratch);
                 }
+                stamp();
                 if (!(last && g == ng - 1)) grid_barrier(A.bar, ++bidx * grid);
+                stamp();
             }
         }
     }

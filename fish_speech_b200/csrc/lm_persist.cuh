@@ -31,6 +31,8 @@ struct PkArgs {
     __nv_bfloat16 *xres, *xn, *attn, *hbuf;
     float* ws;
     unsigned* bar;  // [2]: phase counter, exit counter
+    unsigned long long* trace;  // optional: CTA 0 globaltimer stamps, 4 per GEMM (epilogue done, barrier, consumer done, barrier)
+    int trace_max;
 };
 
 int pk_init();

@@ -155,6 +155,7 @@ class LmEngine:
             "finished": ((self.max_batch,), "<i4"),
             "cur_tok": ((self.max_batch, C1), "<i4"),
             "ras_window": ((self.max_batch, 10), "<i4"),
+            "pk_trace": ((1024,), "<i8"),
             "slow_logits": ((self.max_batch, self.head_rows), "<f4"),
             "fast_logits": ((c.num_codebooks, self.max_batch, c.codebook_size), "<f4"),
             "hidden": ((32 * max(c.dim, c.fast_dim),), "<u2"),
