@@ -190,6 +190,10 @@ int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool
         A.qk_norm = s.qk_norm ? 1 : 0;
         A.kv_only_last = stop_after_kv ? 1 : 0;
         A.stages = h->pk_stages;
+        {
+            const char* e = getenv("FSB_PK_L2PF");
+            A.l2_prefetch = e ? atoi(e) : 24;
+        }
         A.row_seq = c.row_seq;
         A.row_pos = c.row_pos;
         A.freqs = s.freqs;
@@ -549,6 +553,8 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
                 g.cta_items = p.cta_items_dev;
                 g.nparts = p.nparts_dev;
                 g.n_out = p.p.ws_ld;
+                g.max_parts = p.max_parts;
+                g.kblocks = p.p.kb_per_tap;
                 g.slot_stride = p.p.ws_slot_stride;
             };
             for (int l = 0; l < st.nl; ++l) {

@@ -72,7 +72,7 @@ __device__ __forceinline__ void get_item(const PkGemm& G, int n, int& i0, int& k
 
 // ---- producer: stream one GEMM; `it` is the global k-block counter of the ring ----
 __device__ void produce_gemm(const PkGemm& G, const Ring& R, int& it, const unsigned* bar, unsigned need,
-                             bool first) {
+                             bool first, int l2_prefetch) {
     const int item_begin = G.cta_items[blockIdx.x], item_end = G.cta_items[blockIdx.x + 1];
     // pass 1: weight tiles for as many k-blocks as the ring holds
     int pre = 0;
@@ -102,8 +102,39 @@ __device__ void produce_gemm(const PkGemm& G, const Ring& R, int& it, const unsi
     // the activation operand is published by the barrier `need` (or by the upstream kernel for the first GEMM)
     if (first) {
         pdl_wait();
-    } else {
-        spin_until(bar, need);
+    } else if (ld_acquire_u32(bar) < need) {
+        // While the consumers of the previous GEMM are still running HBM would idle: use the wait to pull
+        // the NEXT weight tiles of this CTA's range (beyond what the ring already holds) into L2, paced so
+        // the requests do not pile up in front of other CTAs' demand loads.
+        int n = item_begin, kb = 0, i0 = 0, kb0 = 0, kb1 = 0, slot = 0, skip = pre, issued = 0;
+        if (n < item_end) {
+            get_item(G, n, i0, kb0, kb1, slot);
+            kb = kb0;
+        }
+        const long long t0 = clock64();
+        long long next_t = t0;
+        while (ld_acquire_u32(bar) < need) {
+            const long long now = clock64();
+            if (n < item_end && issued < l2_prefetch && now >= next_t) {
+                if (skip > 0) {
+                    --skip;
+                } else {
+                    tma_prefetch_l2_3d(&G.tmA, kb * kBlockK, i0, 0);
+                    ++issued;
+                    next_t = now + 400;
+                }
+                if (++kb >= kb1) {
+                    if (++n < item_end) {
+                        get_item(G, n, i0, kb0, kb1, slot);
+                        kb = kb0;
+                    }
+                }
+            }
+            if (now - t0 > 4000000000ll) {
+                printf("fsb: producer barrier timeout block=%d have=%u want=%u\n", blockIdx.x, ld_acquire_u32(bar), need);
+                __trap();
+            }
+        }
     }
     fence_proxy_async_all();
     int local = 0;
@@ -193,6 +224,39 @@ __device__ __forceinline__ Partials parts_of(const PkGemm& G, const float* ws) {
     return P;
 }
 
+// Slot-ordered partial sums of N output elements at once: all loads of a 4-slot round are issued before
+// any add, so a thread pays ~max_parts/4 L2 round trips for N elements instead of N * max_parts/4.
+// The additions are in the same order as sum_parts() (bitwise identical results).
+template <int N>
+__device__ __forceinline__ void sum_parts_n(const Partials& P, const int (&row)[N], const int (&feat)[N],
+                                            const bool (&ok)[N], float (&out)[N], int maxp) {
+    int np[N];
+    const float* p[N];
+    const size_t ss = static_cast<size_t>(P.slot_stride);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        np[k] = ok[k] ? (P.nparts ? __ldg(P.nparts + (feat[k] >> 7)) : 1) : 0;
+        p[k] = P.ws + static_cast<size_t>(ok[k] ? row[k] : 0) * P.ld + (ok[k] ? feat[k] : 0);
+        out[k] = 0.f;
+    }
+    for (int q = 0; q < maxp; q += 4) {
+        float a[N][4];
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[k][u] = (q + u < np[k]) ? p[k][static_cast<size_t>(q + u) * ss] : 0.f;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            if (q < np[k]) {
+                out[k] += a[k][0];
+                out[k] += a[k][1];
+                out[k] += a[k][2];
+                out[k] += a[k][3];
+            }
+        }
+    }
+}
+
 // ---- consumer phases (256 worker threads; same rounding points as lm_kernels.cu) ----
 __device__ float worker_sum(float v, float* red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -211,29 +275,38 @@ __device__ void phase_resid_norm(const PkArgs& A, const PkGemm& G, const __nv_bf
                                  const __nv_bfloat16* norm_w, float* scratch) {
     const Partials P = parts_of(G, A.ws);
     const int D = A.D;
+    constexpr int NE = 16;  // D <= 4096
     for (int row = blockIdx.x; row < A.rows; row += gridDim.x) {
-        float v[16];
+        int rws[NE], fts[NE];
+        bool ok[NE];
+        float y[NE], v[NE], xin[NE], nw[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            fts[e] = threadIdx.x + e * kPkWorkers;
+            rws[e] = row;
+            ok[e] = fts[e] < D;
+            xin[e] = ok[e] ? bf2f(A.xres[static_cast<size_t>(row) * D + fts[e]]) : 0.f;
+            nw[e] = ok[e] ? bf2f(norm_w[fts[e]]) : 0.f;
+        }
+        sum_parts_n<NE>(P, rws, fts, ok, y, G.max_parts);
         float ss = 0.f;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const int d = threadIdx.x + e * kPkWorkers;
+        for (int e = 0; e < NE; ++e) {
             v[e] = 0.f;
-            if (d < D) {
-                float y = sum_parts(P, row, d);
-                if (bias) y += bf2f(bias[d]);
-                const float x = rbf(bf2f(A.xres[static_cast<size_t>(row) * D + d]) + rbf(y));
+            if (ok[e]) {
+                float yy = y[e];
+                if (bias) yy += bf2f(bias[fts[e]]);
+                const float x = rbf(xin[e] + rbf(yy));
                 v[e] = x;
                 ss += x * x;
-                A.xres[static_cast<size_t>(row) * D + d] = f2bf(x);
+                A.xres[static_cast<size_t>(row) * D + fts[e]] = f2bf(x);
             }
         }
         const float tot = worker_sum(ss, scratch);
         const float r = rsqrtf(tot / static_cast<float>(D) + A.eps);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const int d = threadIdx.x + e * kPkWorkers;
-            if (d < D) A.xn[static_cast<size_t>(row) * D + d] = f2bf(rbf(rbf(v[e] * r) * bf2f(norm_w[d])));
-        }
+        for (int e = 0; e < NE; ++e)
+            if (ok[e]) A.xn[static_cast<size_t>(row) * D + fts[e]] = f2bf(rbf(rbf(v[e] * r) * nw[e]));
         named_bar_sync(2, kPkWorkers);
     }
 }
@@ -241,53 +314,95 @@ __device__ void phase_resid_norm(const PkArgs& A, const PkGemm& G, const __nv_bf
 __device__ void phase_swiglu(const PkArgs& A, const PkGemm& G) {
     const Partials P = parts_of(G, A.ws);
     const long long total = static_cast<long long>(A.rows) * A.I;
-    for (long long e = static_cast<long long>(blockIdx.x) * kPkWorkers + threadIdx.x; e < total;
-         e += static_cast<long long>(gridDim.x) * kPkWorkers) {
-        const int row = static_cast<int>(e / A.I), i = static_cast<int>(e - static_cast<long long>(row) * A.I);
-        const float g = rbf(sum_parts(P, row, i));
-        const float c = rbf(sum_parts(P, row, A.I + i));
-        const float s = rbf(g / (1.f + expf(-g)));
-        A.hbuf[static_cast<size_t>(row) * A.I + i] = f2bf(s * c);
+    const long long stride = static_cast<long long>(gridDim.x) * kPkWorkers;
+    constexpr int NE = 4;
+    for (long long e0 = static_cast<long long>(blockIdx.x) * kPkWorkers + threadIdx.x; e0 < total; e0 += NE * stride) {
+        int rws[2 * NE], fts[2 * NE];
+        bool ok[2 * NE];
+        float y[2 * NE];
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            const long long e = e0 + k * stride;
+            const bool o = e < total;
+            const int row = o ? static_cast<int>(e / A.I) : 0;
+            const int i = o ? static_cast<int>(e - static_cast<long long>(row) * A.I) : 0;
+            rws[2 * k] = rws[2 * k + 1] = row;
+            fts[2 * k] = i;
+            fts[2 * k + 1] = A.I + i;
+            ok[2 * k] = ok[2 * k + 1] = o;
+        }
+        sum_parts_n<2 * NE>(P, rws, fts, ok, y, G.max_parts);
+#pragma unroll
+        for (int k = 0; k < NE; ++k) {
+            if (ok[2 * k]) {
+                const float g = rbf(y[2 * k]), c = rbf(y[2 * k + 1]);
+                const float sg = rbf(g / (1.f + expf(-g)));
+                A.hbuf[static_cast<size_t>(rws[2 * k]) * A.I + fts[2 * k]] = f2bf(sg * c);
+            }
+        }
     }
 }
 
-// q/k/v post-processing + KV append + attention for one (row, kv-head) item   (llama.py:891-934 / 948-976)
+// q/k/v post-processing + KV append + attention for one (row, kv-head) item   (llama.py:891-934 / 948-976).
+// Each HALF of the worker threads (128 threads, 4 warps) takes its own item, so the 32 x Hkv items of a
+// decode step fit in one round over 2 x #SM half-CTAs.
+constexpr int kHalf = 128, kHalfWarps = 4;
+
 template <int DH, int G>
-__device__ void phase_prep_attn(const PkArgs& A, const PkLayer& L, float* sm, bool kv_only) {
+__device__ void phase_prep_attn(const PkArgs& A, const PkLayer& L, float* sm_all, bool kv_only) {
     const Partials P = parts_of(L.qkv, A.ws);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int NW = kPkWorkers / 32;
+    const int half = threadIdx.x / kHalf, ht = threadIdx.x % kHalf;
+    const int hw = ht >> 5, lane = ht & 31;
+    const int bar_id = 2 + half;
+    const int lcap = A.S;
+    const size_t per_half = static_cast<size_t>(G + 2) * DH + 8 + static_cast<size_t>(G) * lcap +
+                            static_cast<size_t>(kHalfWarps) * G * DH;
+    float* sm = sm_all + half * per_half;
     float* vals = sm;                    // [(G+2)][DH]  q heads, k, v (post norm / rope, bf16-rounded)
     float* hss = vals + (G + 2) * DH;    // [(G+2)] per-head sum of squares
     float* sc = hss + 8;                 // [G][lcap]
-    const int lcap = A.S;
-    float* red = sc + G * lcap;          // [NW][G][DH]
+    float* red = sc + G * lcap;          // [4][G][DH]
     const float scale = rsqrtf(static_cast<float>(DH));
     const int items = A.rows * A.Hkv;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    constexpr int NV = ((G + 2) * DH + kHalf - 1) / kHalf;
+    for (int item = blockIdx.x * 2 + half; item < items; item += gridDim.x * 2) {
         const int row = item / A.Hkv, g = item - row * A.Hkv;
         const int b = A.row_seq[row], pos = A.row_pos[row];
         // 1. raw values: q heads g*G..g*G+G-1, then k head g, then v head g
-        for (int e = threadIdx.x; e < (G + 2) * DH; e += kPkWorkers) {
-            const int hh = e / DH, d = e - hh * DH;
-            const int feat = hh < G ? (g * G + hh) * DH + d
-                                    : (hh == G ? (A.H + g) * DH + d : (A.H + A.Hkv + g) * DH + d);
-            float v = sum_parts(P, row, feat);
-            if (L.bqkv) v += bf2f(L.bqkv[feat]);
-            vals[e] = rbf(v);
+        {
+            int rws[NV], fts[NV];
+            bool ok[NV];
+            float y[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                const int e = ht + k * kHalf;
+                ok[k] = e < (G + 2) * DH;
+                const int hh = ok[k] ? e / DH : 0, d = ok[k] ? e - hh * DH : 0;
+                fts[k] = hh < G ? (g * G + hh) * DH + d : (hh == G ? (A.H + g) * DH + d : (A.H + A.Hkv + g) * DH + d);
+                rws[k] = row;
+            }
+            sum_parts_n<NV>(P, rws, fts, ok, y, L.qkv.max_parts);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                if (ok[k]) {
+                    float v = y[k];
+                    if (L.bqkv) v += bf2f(L.bqkv[fts[k]]);
+                    vals[ht + k * kHalf] = rbf(v);
+                }
+            }
         }
-        named_bar_sync(2, kPkWorkers);
+        named_bar_sync(bar_id, kHalf);
         if (A.qk_norm) {
-            for (int hh = warp; hh < G + 1; hh += NW) {  // q heads and the k head
+            for (int hh = hw; hh < G + 1; hh += kHalfWarps) {  // q heads and the k head
                 float s = 0.f;
                 for (int d = lane; d < DH; d += 32) s += vals[hh * DH + d] * vals[hh * DH + d];
                 s = warp_sum(s);
                 if (lane == 0) hss[hh] = s;
             }
-            named_bar_sync(2, kPkWorkers);
+            named_bar_sync(bar_id, kHalf);
         }
         // 2. norm + RoPE on pairs, write K/V to the cache
-        for (int e = threadIdx.x; e < (G + 2) * DH / 2; e += kPkWorkers) {
+        for (int e = ht; e < (G + 2) * DH / 2; e += kHalf) {
             const int hh = e / (DH / 2), t = e - hh * (DH / 2);
             float v0 = vals[hh * DH + 2 * t], v1 = vals[hh * DH + 2 * t + 1];
             if (hh <= G) {
@@ -298,9 +413,9 @@ __device__ void phase_prep_attn(const PkArgs& A, const PkLayer& L, float* sm, bo
                     v1 = rbf(v1 * r * bf2f(nw[2 * t + 1]));
                 }
                 const __nv_bfloat16* f = A.freqs + (static_cast<size_t>(pos) * (DH / 2) + t) * 2;
-                const float c = bf2f(f[0]), s = bf2f(f[1]);
-                const float o0 = __fsub_rn(__fmul_rn(v0, c), __fmul_rn(v1, s));
-                const float o1 = __fadd_rn(__fmul_rn(v1, c), __fmul_rn(v0, s));
+                const float c = bf2f(f[0]), sn = bf2f(f[1]);
+                const float o0 = __fsub_rn(__fmul_rn(v0, c), __fmul_rn(v1, sn));
+                const float o1 = __fadd_rn(__fmul_rn(v1, c), __fmul_rn(v0, sn));
                 v0 = rbf(o0);
                 v1 = rbf(o1);
             }
@@ -310,14 +425,13 @@ __device__ void phase_prep_attn(const PkArgs& A, const PkLayer& L, float* sm, bo
                     cache + ((static_cast<size_t>(b) * A.Hkv + g) * A.S + pos) * DH);
                 dst[t] = pack_bf2(v0, v1);
             }
-            // keep the processed values for the attention below (scores of position `pos` use them too)
             vals[hh * DH + 2 * t] = v0;
             vals[hh * DH + 2 * t + 1] = v1;
         }
         __threadfence_block();
-        named_bar_sync(2, kPkWorkers);
+        named_bar_sync(bar_id, kHalf);
         if (kv_only) continue;
-        // 3. attention over cache positions [0, pos] (the row for `pos` was just written by this CTA)
+        // 3. attention over cache positions [0, pos] (the row for `pos` was just written by this half-CTA)
         const int Lq = pos + 1;
         const size_t cache_base = (static_cast<size_t>(b) * A.Hkv + g) * A.S * DH;
         const __nv_bfloat16* kc = L.kcache + cache_base;
@@ -329,7 +443,7 @@ __device__ void phase_prep_attn(const PkArgs& A, const PkLayer& L, float* sm, bo
         for (int gg = 0; gg < G; ++gg)
 #pragma unroll
             for (int e = 0; e < 8; ++e) qr[gg][e] = vals[gg * DH + li * 8 + e];
-        for (int pb = warp * RPW * UNR; pb < Lq; pb += NW * RPW * UNR) {
+        for (int pb = hw * RPW * UNR; pb < Lq; pb += kHalfWarps * RPW * UNR) {
             uint4 u[UNR];
 #pragma unroll
             for (int j = 0; j < UNR; ++j) {
@@ -340,7 +454,7 @@ __device__ void phase_prep_attn(const PkArgs& A, const PkLayer& L, float* sm, bo
 #pragma unroll
             for (int j = 0; j < UNR; ++j) {
                 const int p = pb + j * RPW + sub;
-                const bool ok = p < Lq;
+                const bool okp = p < Lq;
                 const float kf[8] = {bf_lo(u[j].x), bf_hi(u[j].x), bf_lo(u[j].y), bf_hi(u[j].y),
                                      bf_lo(u[j].z), bf_hi(u[j].z), bf_lo(u[j].w), bf_hi(u[j].w)};
 #pragma unroll
@@ -350,12 +464,12 @@ __device__ void phase_prep_attn(const PkArgs& A, const PkLayer& L, float* sm, bo
                     for (int e = 0; e < 8; ++e) d += qr[gg][e] * kf[e];
 #pragma unroll
                     for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                    if (ok && li == 0) sc[gg * lcap + p] = A.bf16_math ? rbf(rbf(d) * scale) : d * scale;
+                    if (okp && li == 0) sc[gg * lcap + p] = A.bf16_math ? rbf(rbf(d) * scale) : d * scale;
                 }
             }
         }
-        named_bar_sync(2, kPkWorkers);
-        for (int gg = warp; gg < G; gg += NW) {
+        named_bar_sync(bar_id, kHalf);
+        for (int gg = hw; gg < G; gg += kHalfWarps) {
             float* s = sc + gg * lcap;
             float m = -INFINITY;
             for (int p = lane; p < Lq; p += 32) m = fmaxf(m, s[p]);
@@ -372,18 +486,18 @@ __device__ void phase_prep_attn(const PkArgs& A, const PkLayer& L, float* sm, bo
                 s[p] = A.bf16_math ? rbf(pr) : pr;
             }
         }
-        named_bar_sync(2, kPkWorkers);
+        named_bar_sync(bar_id, kHalf);
         constexpr int DPL = DH / 32;
         float acc[G][DPL];
 #pragma unroll
         for (int gg = 0; gg < G; ++gg)
 #pragma unroll
             for (int e = 0; e < DPL; ++e) acc[gg][e] = 0.f;
-        for (int pb = warp; pb < Lq; pb += NW * UNR) {
+        for (int pb = hw; pb < Lq; pb += kHalfWarps * UNR) {
             float vf[UNR][DPL];
 #pragma unroll
             for (int j = 0; j < UNR; ++j) {
-                const int p = pb + j * NW;
+                const int p = pb + j * kHalfWarps;
 #pragma unroll
                 for (int e = 0; e < DPL; ++e) vf[j][e] = 0.f;
                 if (p < Lq) {
@@ -398,7 +512,7 @@ __device__ void phase_prep_attn(const PkArgs& A, const PkLayer& L, float* sm, bo
             }
 #pragma unroll
             for (int j = 0; j < UNR; ++j) {
-                const int p = pb + j * NW;
+                const int p = pb + j * kHalfWarps;
                 if (p < Lq) {
 #pragma unroll
                     for (int gg = 0; gg < G; ++gg) {
@@ -412,16 +526,16 @@ __device__ void phase_prep_attn(const PkArgs& A, const PkLayer& L, float* sm, bo
 #pragma unroll
         for (int gg = 0; gg < G; ++gg)
 #pragma unroll
-            for (int e = 0; e < DPL; ++e) red[(warp * G + gg) * DH + lane * DPL + e] = acc[gg][e];
-        named_bar_sync(2, kPkWorkers);
-        for (int e = threadIdx.x; e < G * DH; e += kPkWorkers) {
+            for (int e = 0; e < DPL; ++e) red[(hw * G + gg) * DH + lane * DPL + e] = acc[gg][e];
+        named_bar_sync(bar_id, kHalf);
+        for (int e = ht; e < G * DH; e += kHalf) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) s += red[w * G * DH + e];
+            for (int w = 0; w < kHalfWarps; ++w) s += red[w * G * DH + e];
             const int gg = e / DH, d = e - gg * DH;
             A.attn[(static_cast<size_t>(row) * A.H + g * G + gg) * DH + d] = f2bf(s);
         }
-        named_bar_sync(2, kPkWorkers);
+        named_bar_sync(bar_id, kHalf);
     }
 }
 
@@ -471,7 +585,7 @@ __global__ void __launch_bounds__(kPkThreads, 1) stack_kernel(const __grid_const
                 const int ng = (l == A.nl - 1) ? ngemm_last : 4;
                 for (int g = 0; g < ng; ++g, ++n) {
                     const PkGemm& G2 = g == 0 ? L.qkv : (g == 1 ? L.wo : (g == 2 ? L.w13 : L.w2));
-                    produce_gemm(G2, R, it, A.bar, 2u * n * grid, n == 0);
+                    produce_gemm(G2, R, it, A.bar, 2u * n * grid, n == 0, A.l2_prefetch);
                 }
             }
         }
@@ -560,7 +674,8 @@ int launch_t(const PkArgs& A, int grid, size_t smem, cudaStream_t st) {
 
 size_t pk_scratch_bytes(int H, int Hkv, int Dh, int S) {
     const int G = H / Hkv;
-    return (static_cast<size_t>(G + 2) * Dh + 8 + static_cast<size_t>(G) * S + static_cast<size_t>(8) * G * Dh) * sizeof(float) + 64;
+    // two half-CTA work areas of the attention phase
+    return 2 * (static_cast<size_t>(G + 2) * Dh + 8 + static_cast<size_t>(G) * S + static_cast<size_t>(4) * G * Dh) * sizeof(float) + 64;
 }
 
 int pk_init() {

@@ -10,6 +10,8 @@ struct PkGemm {            // one weight-streaming GEMM inside the persistent ke
     const int* cta_items;  // [grid + 1]
     const int* nparts;     // partial count per 128-feature tile
     int n_out;
+    int max_parts;
+    int kblocks;  // k-blocks per tile
     int pad;
     long long slot_stride;
 };
@@ -25,6 +27,7 @@ struct PkArgs {
     int nl, rows, D, H, Hkv, Dh, I, S;
     float eps;
     int bf16_math, qk_norm, kv_only_last, stages;
+    int l2_prefetch;  // weight tiles per CTA prefetched into L2 while the producer waits for a barrier
     const int* row_seq;
     const int* row_pos;
     const __nv_bfloat16* freqs;
