@@ -425,6 +425,7 @@ int fsb_resid_scale_norm(const float* d_y, int ld, const void* d_scale, const vo
     ResidNormArgs a{};
     a.parts.ws = d_y;
     a.parts.ld = ld;
+    a.parts.max_parts = 1;
     a.scale = reinterpret_cast<const bf16*>(d_scale);
     a.x_in = reinterpret_cast<const bf16*>(d_x_in);
     a.x_out = reinterpret_cast<bf16*>(d_x_out);

@@ -153,6 +153,7 @@ Partials parts_of(const GemmPlan& p) {
     P.slot_stride = p.p.ws_slot_stride;
     P.ld = p.p.ws_ld;
     P.nparts = p.nparts_dev;
+    P.max_parts = p.max_parts;
     return P;
 }
 

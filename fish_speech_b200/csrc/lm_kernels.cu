@@ -45,24 +45,33 @@ __global__ void __launch_bounds__(kRnThreads) resid_norm_kernel(ResidNormArgs a,
     const int row = blockIdx.x;
     const int grow = a.gather_map ? a.gather_map[row] : row;
     const int src = a.gather ? a.gather[static_cast<size_t>(grow) * gstride] : row;
-    float v[kRnMaxPer];
+    float v[kRnMaxPer], y[kRnMaxPer];
+    int rws[kRnMaxPer], fts[kRnMaxPer];
+    bool ok[kRnMaxPer];
+#pragma unroll
+    for (int e = 0; e < kRnMaxPer; ++e) {
+        fts[e] = threadIdx.x + e * kRnThreads;
+        rws[e] = row;
+        ok[e] = fts[e] < a.D;
+        v[e] = (ok[e] && a.x_in) ? bf2f(a.x_in[static_cast<size_t>(src) * a.D + fts[e]]) : 0.f;
+        y[e] = 0.f;
+    }
+    if (a.parts.ws) sum_parts_n<kRnMaxPer>(a.parts, rws, fts, ok, y, a.parts.max_parts > 0 ? a.parts.max_parts : 1);
     float ss = 0.f;
 #pragma unroll
     for (int e = 0; e < kRnMaxPer; ++e) {
-        const int d = threadIdx.x + e * kRnThreads;
-        v[e] = 0.f;
-        if (d < a.D) {
-            float x = a.x_in ? bf2f(a.x_in[static_cast<size_t>(src) * a.D + d]) : 0.f;
+        if (ok[e]) {
+            float x = v[e];
             if (a.parts.ws) {
-                float y = sum_parts(a.parts, row, d);
-                if (a.bias) y += bf2f(a.bias[d]);
-                y = rbf(y);
-                if (a.scale) y *= bf2f(a.scale[d]);
-                x = rbf(x + y);
+                float yy = y[e];
+                if (a.bias) yy += bf2f(a.bias[fts[e]]);
+                yy = rbf(yy);
+                if (a.scale) yy *= bf2f(a.scale[fts[e]]);
+                x = rbf(x + yy);
             }
             v[e] = x;
             ss += x * x;
-            if (a.x_out) a.x_out[static_cast<size_t>(row) * a.D + d] = f2bf(x);
+            if (a.x_out) a.x_out[static_cast<size_t>(row) * a.D + fts[e]] = f2bf(x);
         }
     }
     if (a.norm_w == nullptr) return;
@@ -70,10 +79,9 @@ __global__ void __launch_bounds__(kRnThreads) resid_norm_kernel(ResidNormArgs a,
     const float r = rsqrtf(tot / static_cast<float>(a.D) + a.eps);
 #pragma unroll
     for (int e = 0; e < kRnMaxPer; ++e) {
-        const int d = threadIdx.x + e * kRnThreads;
-        if (d < a.D) {
-            const float n = rbf(rbf(v[e] * r) * bf2f(a.norm_w[d]));
-            a.n_out[static_cast<size_t>(row) * a.D + d] = f2bf(n);
+        if (ok[e]) {
+            const float n = rbf(rbf(v[e] * r) * bf2f(a.norm_w[fts[e]]));
+            a.n_out[static_cast<size_t>(row) * a.D + fts[e]] = f2bf(n);
         }
     }
 }
@@ -101,7 +109,15 @@ __global__ void qkv_prep_kernel(QkvPrepArgs a) {
     const int Dh = a.Dh;
     const int kind = head < a.H ? 0 : (head < a.H + a.Hkv ? 1 : 2);  // q, k, v
     const int f0 = head * Dh + 2 * t;
-    float v0 = sum_parts(a.parts, row, f0), v1 = sum_parts(a.parts, row, f0 + 1);
+    float v0, v1;
+    {
+        const int rws[2] = {row, row}, fts[2] = {f0, f0 + 1};
+        const bool ok[2] = {true, true};
+        float y[2];
+        sum_parts_n<2>(a.parts, rws, fts, ok, y, a.parts.max_parts > 0 ? a.parts.max_parts : 1);
+        v0 = y[0];
+        v1 = y[1];
+    }
     if (a.bias) {
         v0 += bf2f(a.bias[f0]);
         v1 += bf2f(a.bias[f0 + 1]);
@@ -284,8 +300,11 @@ __global__ void swiglu_kernel(SwigluArgs a) {
     const int row = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.I) return;
-    const float g = rbf(sum_parts(a.parts, row, i));
-    const float c = rbf(sum_parts(a.parts, row, a.I + i));
+    const int rws[2] = {row, row}, fts[2] = {i, a.I + i};
+    const bool ok[2] = {true, true};
+    float y[2];
+    sum_parts_n<2>(a.parts, rws, fts, ok, y, a.parts.max_parts > 0 ? a.parts.max_parts : 1);
+    const float g = rbf(y[0]), c = rbf(y[1]);
     const float s = rbf(g / (1.f + expf(-g)));
     a.h[static_cast<size_t>(row) * a.I + i] = f2bf(s * c);
 }

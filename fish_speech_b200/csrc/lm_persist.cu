@@ -221,40 +221,8 @@ __device__ __forceinline__ Partials parts_of(const PkGemm& G, const float* ws) {
     P.slot_stride = G.slot_stride;
     P.ld = G.n_out;
     P.nparts = G.nparts;
+    P.max_parts = G.max_parts;
     return P;
-}
-
-// Slot-ordered partial sums of N output elements at once: all loads of a 4-slot round are issued before
-// any add, so a thread pays ~max_parts/4 L2 round trips for N elements instead of N * max_parts/4.
-// The additions are in the same order as sum_parts() (bitwise identical results).
-template <int N>
-__device__ __forceinline__ void sum_parts_n(const Partials& P, const int (&row)[N], const int (&feat)[N],
-                                            const bool (&ok)[N], float (&out)[N], int maxp) {
-    int np[N];
-    const float* p[N];
-    const size_t ss = static_cast<size_t>(P.slot_stride);
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        np[k] = ok[k] ? (P.nparts ? __ldg(P.nparts + (feat[k] >> 7)) : 1) : 0;
-        p[k] = P.ws + static_cast<size_t>(ok[k] ? row[k] : 0) * P.ld + (ok[k] ? feat[k] : 0);
-        out[k] = 0.f;
-    }
-    for (int q = 0; q < maxp; q += 4) {
-        float a[N][4];
-#pragma unroll
-        for (int k = 0; k < N; ++k)
-#pragma unroll
-            for (int u = 0; u < 4; ++u) a[k][u] = (q + u < np[k]) ? p[k][static_cast<size_t>(q + u) * ss] : 0.f;
-#pragma unroll
-        for (int k = 0; k < N; ++k) {
-            if (q < np[k]) {
-                out[k] += a[k][0];
-                out[k] += a[k][1];
-                out[k] += a[k][2];
-                out[k] += a[k][3];
-            }
-        }
-    }
 }
 
 // ---- consumer phases (256 worker threads; same rounding points as lm_kernels.cu) ----
