@@ -236,5 +236,9 @@ class LmEngine:
                 self._inflight = (d_tok, d_slot, d_pos, d_last, d_gsl)
 
     def decode(self, batch: int, nframes: int, sp: _lib.Sampling, use_graph: bool = True) -> None:
+        import os
+
+        if os.environ.get("FSB_NO_GRAPH") == "1":  # diagnostic: eager launches instead of graph replays
+            use_graph = False
         with torch.cuda.device(self.device):
             _lib.check(self.lib.fsb_lm_decode(self.h, batch, nframes, C.byref(sp), int(use_graph), _stream()))
