@@ -424,8 +424,7 @@ def launch_thread_safe_queue(checkpoint_path, device, precision, compile: bool =
 
     def worker():
         model, decode_one_token = init_model(checkpoint_path, device, precision, compile=compile)
-        with torch.cuda.device(device):
-            model.setup_caches(max_batch_size=1, max_seq_len=model.config.max_seq_len, dtype=model.dtype)
+        model.setup_caches(max_batch_size=1, max_seq_len=model.config.max_seq_len, dtype=model.dtype)
         init_event.set()
         while True:
             item: Optional[GenerateRequest] = input_queue.get()
