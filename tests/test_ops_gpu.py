@@ -1,0 +1,161 @@
+"""Per-op parity of the glue kernels through the C-ABI (fp32 GEMM results in, bf16 operands out) against
+plain PyTorch fp32 references of the same op with the reference's rounding points."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _lib():
+    from fish_speech_b200 import _lib
+
+    return _lib, _lib.lib()
+
+
+def rbf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("rows,D", [(1, 256), (32, 2560), (7, 1024)])
+def test_resid_scale_norm(rows, D):
+    _l, L = _lib()
+    g = torch.Generator().manual_seed(rows * D)
+    y = torch.randn(rows, D, generator=g)
+    x = torch.randn(rows, D, generator=g).bfloat16()
+    scale = (0.3 + 0.1 * torch.randn(D, generator=g)).bfloat16()
+    w = (1 + 0.1 * torch.randn(D, generator=g)).bfloat16()
+    # reference: x' = rbf(x + rbf(y) * scale); n = rbf(rbf(x' * rsqrt(mean(x'^2) + eps)) * w)   (llama.py:990-1001)
+    xr = rbf(x.float() + rbf(y) * scale.float())
+    n = rbf(rbf(xr * torch.rsqrt((xr * xr).mean(-1, keepdim=True) + 1e-5)) * w.float())
+    dy, dx, ds, dw = y.cuda(), x.cuda(), scale.cuda(), w.cuda()
+    xo, no = torch.empty_like(dx), torch.empty_like(dx)
+    _l.check(L.fsb_resid_scale_norm(dy.data_ptr(), D, ds.data_ptr(), dx.data_ptr(), xo.data_ptr(), dw.data_ptr(),
+                                    no.data_ptr(), rows, D, 1e-5, 0, _st()))
+    torch.cuda.synchronize()
+    assert torch.equal(xo.cpu().float(), xr)
+    # the row reduction order differs from torch's: allow one bf16 ulp on a handful of elements
+    diff = (no.cpu().float() - n).abs()
+    assert (diff > 0).float().mean() < 0.02 and diff.max() <= 2 ** -6 * n.abs().max()
+
+
+@pytest.mark.parametrize("rows,I", [(3, 512), (32, 9728)])
+def test_swiglu(rows, I):
+    _l, L = _lib()
+    g = torch.Generator().manual_seed(I)
+    y = torch.randn(rows, 2 * I, generator=g) * 2
+    a, c = rbf(y[:, :I]), rbf(y[:, I:])
+    ref = rbf(rbf(a / (1 + torch.exp(-a))) * c)
+    dy = y.cuda()
+    h = torch.empty(rows, I, dtype=torch.bfloat16, device="cuda")
+    _l.check(L.fsb_swiglu_f32(dy.data_ptr(), rows, I, h.data_ptr(), _st()))
+    torch.cuda.synchronize()
+    diff = (h.cpu().float() - ref).abs()
+    assert (diff > 0).float().mean() < 0.01 and diff.max() <= 2 ** -6 * ref.abs().max()  # expf vs torch.exp: rare 1-ulp flips
+
+
+@pytest.mark.parametrize("H,Hkv,Dh,T,window", [(4, 4, 64, 40, 16), (8, 2, 128, 33, 0), (16, 16, 64, 150, 128)])
+def test_qkv_rope_and_window_attention(H, Hkv, Dh, T, window):
+    """qkv post-processing (RoPE with a bf16 table, cache write) + banded causal attention vs torch SDPA."""
+    _l, L = _lib()
+    B = 2
+    rows = B * T
+    g = torch.Generator().manual_seed(H * T)
+    qkv = torch.randn(rows, (H + 2 * Hkv) * Dh, generator=g)
+    inv = 1.0 / (10000 ** (torch.arange(0, Dh, 2).float() / Dh))
+    ang = torch.outer(torch.arange(T), inv)
+    freqs = torch.stack([torch.cos(ang), torch.sin(ang)], -1).bfloat16()
+    seq = torch.arange(B, dtype=torch.int32).repeat_interleave(T)
+    pos = torch.arange(T, dtype=torch.int32).repeat(B)
+    d = lambda t: t.cuda()
+    dq = torch.empty(rows, H, Dh, dtype=torch.bfloat16, device="cuda")
+    dk = torch.zeros(B, Hkv, T, Dh, dtype=torch.bfloat16, device="cuda")
+    dv = torch.zeros_like(dk)
+    dqkv, dfr, dseq, dpos = d(qkv), d(freqs), d(seq), d(pos)
+    _l.check(L.fsb_qkv_rope(dqkv.data_ptr(), rows, H, Hkv, Dh, dfr.data_ptr(), dseq.data_ptr(), dpos.data_ptr(),
+                            dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), T, _st()))
+    out = torch.empty(rows, H * Dh, dtype=torch.bfloat16, device="cuda")
+    _l.check(L.fsb_window_attn(dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dseq.data_ptr(), dpos.data_ptr(), rows, H,
+                               Hkv, Dh, T, window, out.data_ptr(), _st()))
+    torch.cuda.synchronize()
+
+    # reference (llama.py:1026-1038 rotary, modded_dac.py:380-398 window mask)
+    def rope(x):  # [B,T,h,Dh]
+        xs = x.float().reshape(*x.shape[:-1], -1, 2)
+        fr = freqs.float().view(1, T, 1, Dh // 2, 2)
+        o = torch.stack([xs[..., 0] * fr[..., 0] - xs[..., 1] * fr[..., 1],
+                         xs[..., 1] * fr[..., 0] + xs[..., 0] * fr[..., 1]], -1)
+        return rbf(o.flatten(3))
+
+    q, k, v = rbf(qkv).view(B, T, -1).split([H * Dh, Hkv * Dh, Hkv * Dh], -1)
+    q, k, v = rope(q.view(B, T, H, Dh)), rope(k.view(B, T, Hkv, Dh)), v.view(B, T, Hkv, Dh)
+    assert torch.equal(dq.cpu().float().view(B, T, H, Dh), q)
+    assert torch.equal(dk.cpu().float().transpose(1, 2), k)
+    idx = torch.arange(T)
+    mask = idx[None, :] <= idx[:, None]
+    if window:
+        mask &= idx[None, :] >= (idx[:, None] - window + 1)
+    kk = k.transpose(1, 2).repeat_interleave(H // Hkv, dim=1)
+    vv = v.transpose(1, 2).repeat_interleave(H // Hkv, dim=1)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), kk, vv, attn_mask=mask)
+    ref = ref.transpose(1, 2).reshape(rows, H * Dh)
+    err = (out.cpu().float() - ref).abs().max().item()
+    assert err <= 2 ** -7 * ref.abs().max().item() + 1e-3, err
+
+
+@pytest.mark.parametrize("rows,K,N", [(5, 256, 384), (300, 1024, 3072), (32, 9728, 2560)])
+def test_linear_f32(rows, K, N):
+    _l, L = _lib()
+    g = torch.Generator().manual_seed(K)
+    x = (torch.randn(rows, K, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.05).bfloat16()
+    ref = x.float() @ w.float().t()
+    dx, dw = x.cuda(), w.cuda()
+    ws = torch.empty(rows, N, device="cuda")
+    _l.check(L.fsb_linear_f32(dx.data_ptr(), rows, K, dw.data_ptr(), N, ws.data_ptr(), _st()))
+    torch.cuda.synchronize()
+    assert (ws.cpu() - ref).abs().max() <= 2e-3 * max(1.0, ref.abs().max())
+
+
+def test_conv_gemm_causal_dilated_and_transposed():
+    """fsb_conv_gemm against F.conv1d / F.conv_transpose1d with the codec's causal padding rules."""
+    from fish_speech_b200.models.dac.modded_dac import DAC, CodecConfig
+
+    B, T, Cin, Cout = 2, 300, 96, 192
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, Cin, T, generator=g).bfloat16().float()
+    dac = object.__new__(DAC)
+    dac._device = torch.device("cuda")
+    dac._keep, dac._bufs = [], {}
+    from fish_speech_b200 import _lib as _l
+
+    dac.lib = _l.lib()
+    for dil in (1, 3, 9):
+        w = (torch.randn(Cout, Cin, 7, generator=g) / math.sqrt(7 * Cin)).bfloat16().float()
+        b = torch.randn(Cout, generator=g) * 0.1
+        dac._sd = {"c.weight": w, "c.bias": b}
+        cv = dac._conv("c", dilation=dil)
+        xin = x.transpose(1, 2).contiguous().bfloat16().cuda()  # [B][T][C]
+        out = torch.empty(B, T, Cout, dtype=torch.bfloat16, device="cuda")
+        dac._gemm(cv, xin, B, T, Cin, T, out0=out)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.conv1d(torch.nn.functional.pad(x, (6 * dil, 0)), w, b, dilation=dil)
+        err = (out.cpu().float().transpose(1, 2) - ref).abs().max().item()
+        assert err <= 2e-2 * max(1.0, ref.abs().max().item()), (dil, err)
+    # transposed conv k = 2 * stride, right trim k - stride (modded_dac.py:574-580)
+    s = 4
+    wt = (torch.randn(Cin, Cout, 2 * s, generator=g) / math.sqrt(2 * Cin)).bfloat16().float()
+    bt = torch.randn(Cout, generator=g) * 0.1
+    dac._sd = {"t.weight": wt, "t.bias": bt}
+    cv = dac._convT("t", s)
+    out = torch.empty(B, T * s, Cout, dtype=torch.bfloat16, device="cuda")
+    dac._gemm(cv, xin, B, T, Cin, T, out0=out)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv_transpose1d(x, wt, bt, stride=s)[..., : T * s]
+    err = (out.cpu().float().transpose(1, 2) - ref).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), err
