@@ -77,6 +77,7 @@ struct fsb_lm {
     float *slow_logits = nullptr, *fast_logits = nullptr;
     bf16* dbg_x = nullptr;
     bool persistent = false;
+    bool fused_prep_attn = true;
     int pk_stages = 8;
     unsigned* pk_bar = nullptr;
     unsigned long long* pk_trace = nullptr;
@@ -210,6 +211,37 @@ int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool
         const LayerW& w = s.w[l];
         LayerPlans& P = c.decode ? s.dec[l] : s.pf[l];
         FSB_TRY(launch_rows(P.qkv, c.rows, st));
+        if (c.decode && h->fused_prep_attn) {
+            // decode rows: q/k/v post-processing, KV append and attention in one launch
+            PkArgs A{};
+            A.rows = c.rows; A.D = s.D; A.H = s.H; A.Hkv = s.Hkv; A.Dh = s.Dh; A.I = s.I; A.S = s.S;
+            A.eps = eps;
+            A.bf16_math = s.bf16_math;
+            A.qk_norm = s.qk_norm ? 1 : 0;
+            A.row_seq = c.row_seq;
+            A.row_pos = c.row_pos;
+            A.freqs = s.freqs;
+            A.attn = c.attn;
+            A.ws = h->ws;
+            PkLayer L{};
+            L.qkv.nparts = P.qkv.nparts_dev;
+            L.qkv.n_out = P.qkv.p.ws_ld;
+            L.qkv.max_parts = P.qkv.max_parts;
+            L.qkv.slot_stride = P.qkv.p.ws_slot_stride;
+            L.bqkv = w.bqkv;
+            L.q_norm = s.qk_norm ? w.q_norm : nullptr;
+            L.k_norm = s.qk_norm ? w.k_norm : nullptr;
+            L.kcache = s.kcache + l * s.cache_layer_stride;
+            L.vcache = s.vcache + l * s.cache_layer_stride;
+            const bool kv_only = stop_after_kv && l == s.nl - 1;
+            const int rc = launch_prep_attn(A, L, kv_only ? 1 : 0, st);
+            if (rc > 0) return rc;
+            if (rc == 0) {
+                if (kv_only) return 0;
+                goto after_attention;
+            }
+        }
+        {
         QkvPrepArgs qa{};
         qa.parts = parts_of(P.qkv);
         qa.bias = w.bqkv;
@@ -236,6 +268,8 @@ int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool
         aa.window = 0;
         aa.bf16_math = s.bf16_math;
         FSB_TRY(launch_attn(aa, st));
+        }
+    after_attention:
         FSB_TRY(launch_rows(P.wo, c.rows, st));
         ResidNormArgs r1{};
         r1.parts = parts_of(P.wo);
@@ -539,8 +573,12 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
         const char* es = getenv("FSB_PK_STAGES");
         if (es) h->pk_stages = atoi(es);
     }
-    if (h->persistent) {
+    {
+        const char* ef = getenv("FSB_FUSED_ATTN");
+        h->fused_prep_attn = !(ef && ef[0] == '0');
         TRYC(pk_init());
+    }
+    if (h->persistent) {
         TRYC(dalloc(h, &h->pk_bar, 2));
         if (getenv("FSB_PK_TRACE")) TRYC(dalloc(h, &h->pk_trace, 1024, "pk_trace"));
         auto build_pk = [&](Stack& st, const bf16* final_norm) -> int {

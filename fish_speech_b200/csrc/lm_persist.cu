@@ -626,6 +626,27 @@ __global__ void __launch_bounds__(kPkThreads, 1) stack_kernel(const __grid_const
     }
 }
 
+// Stand-alone use of the fused q/k/v post-processing + KV append + attention phase (default decode path):
+// one launch per layer instead of qkv_prep + attn.
+template <int DH, int G>
+__global__ void __launch_bounds__(kPkWorkers) prep_attn_kernel(const __grid_constant__ PkArgs A,
+                                                               const __grid_constant__ PkLayer L, int kv_only) {
+    extern __shared__ uint8_t pa_smem[];
+    pdl_launch_dependents();
+    pdl_wait();
+    phase_prep_attn<DH, G>(A, L, reinterpret_cast<float*>(pa_smem), kv_only != 0);
+}
+
+template <int DH, int G>
+int launch_pa_t(const PkArgs& A, const PkLayer& L, int kv_only, cudaStream_t st) {
+    const size_t smem = pk_scratch_bytes(A.H, A.Hkv, A.Dh, A.S);
+    FSB_CHECK(smem <= 200 * 1024, "prep_attn: context %d too long for the shared-memory score buffer", A.S);
+    const int items = A.rows * A.Hkv;
+    auto k = prep_attn_kernel<DH, G>;
+    FSB_LAUNCH(k, dim3((items + 1) / 2), dim3(kPkWorkers), smem, st, A, L, kv_only);
+    return 0;
+}
+
 template <int DH, int G>
 int launch_t(const PkArgs& A, int grid, size_t smem, cudaStream_t st) {
     static bool attr = false;
@@ -647,11 +668,22 @@ size_t pk_scratch_bytes(int H, int Hkv, int Dh, int S) {
 }
 
 int pk_init() {
-#define FSB_PK_ATTR(DH_, G_) \
+#define FSB_PK_ATTR(DH_, G_)                                                                                       \
+    FSB_CUDA(cudaFuncSetAttribute(prep_attn_kernel<DH_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
     FSB_CUDA(cudaFuncSetAttribute(stack_kernel<DH_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     FSB_PK_ATTR(128, 4) FSB_PK_ATTR(128, 1) FSB_PK_ATTR(128, 2) FSB_PK_ATTR(64, 4) FSB_PK_ATTR(64, 1) FSB_PK_ATTR(64, 2)
 #undef FSB_PK_ATTR
     return 0;
+}
+
+int launch_prep_attn(const PkArgs& A, const PkLayer& L, int kv_only, cudaStream_t st) {
+    if (A.rows <= 0) return 0;
+    const int G = A.H / A.Hkv;
+#define FSB_PA_CASE(DH_, G_) \
+    if (A.Dh == DH_ && G == G_) return launch_pa_t<DH_, G_>(A, L, kv_only, st);
+    FSB_PA_CASE(128, 4) FSB_PA_CASE(128, 1) FSB_PA_CASE(128, 2) FSB_PA_CASE(64, 4) FSB_PA_CASE(64, 1) FSB_PA_CASE(64, 2)
+#undef FSB_PA_CASE
+    return -1;  // unsupported shape: caller falls back to the two-kernel sequence
 }
 
 int launch_stack_persistent(const PkArgs& A, int grid, cudaStream_t st) {

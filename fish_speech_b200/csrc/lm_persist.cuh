@@ -41,5 +41,7 @@ struct PkArgs {
 int pk_init();
 size_t pk_scratch_bytes(int H, int Hkv, int Dh, int S);
 int launch_stack_persistent(const PkArgs& A, int grid, cudaStream_t st);
+// fused qkv post-processing + KV append + attention for decode rows; returns -1 if the head shape has no instance
+int launch_prep_attn(const PkArgs& A, const PkLayer& L, int kv_only, cudaStream_t st);
 
 }  // namespace fsb
