@@ -186,6 +186,76 @@ def cpu_reference_port(steps: int, warmup: int, frames_per_step: int = 4):
                                f"{cores} threads, layer weights aliased; audio-s/s = frames*2048/44100/time")
 
 
+def voice_clone_bench(args):
+    """BASELINE configs[4], single GPU: every step encodes the 10 s reference clips,
+    builds the prompts (text ids + the reference's VQ columns + text ids), generates 512 frames per utterance
+    and decodes them to waveform — all through the public API, host audio in, host waveform out."""
+    from fish_speech_b200 import synthetic
+    from fish_speech_b200.configs import S2PRO_IM_END_ID, s2pro_args
+    from fish_speech_b200.models.dac.inference import load_codec_config
+    from fish_speech_b200.models.dac.modded_dac import DAC
+    from fish_speech_b200.models.text2semantic.inference import generate_batch
+    from fish_speech_b200.models.text2semantic.llama import DualARTransformer
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, NF, REF_S = 8, 512, 10
+    cfg = s2pro_args(max_seq_len=1024)
+    w = synthetic.lm_state_dict(cfg, dev)
+    w["embeddings.weight"][S2PRO_IM_END_ID] = 0
+    model = DualARTransformer(cfg, w, device=dev, im_end_id=S2PRO_IM_END_ID)
+    model.max_rows = 4096
+    model.setup_caches(max_batch_size=B, max_seq_len=cfg.max_seq_len)
+    del w
+    ccfg = load_codec_config("modded_dac_vq")
+    dac = DAC(ccfg, synthetic.codec_state_dict(ccfg, dev), device=dev)
+    g = torch.Generator().manual_seed(0)
+    audio_host = (0.1 * torch.randn(B, 1, 44100 * REF_S, generator=g)).pin_memory()
+    text_a = [torch.randint(0, 151643, (64,), generator=g, dtype=torch.int32) for _ in range(B)]
+    text_b = [torch.randint(0, 151643, (64,), generator=g, dtype=torch.int32) for _ in range(B)]
+    C = cfg.num_codebooks
+
+    def step():
+        codes, lens = dac.encode(audio_host.to(dev, non_blocking=True))  # [B, 10, 216]
+        prompts = []
+        for b in range(B):
+            T = int(lens[b])
+            vq = torch.zeros(C + 1, T, dtype=torch.int32, device=dev)
+            vq[0] = codes[b, 0, :T].to(torch.int32) + cfg.semantic_begin_id
+            vq[1:] = codes[b, :, :T].to(torch.int32)
+            ta = torch.zeros(C + 1, 64, dtype=torch.int32, device=dev)
+            ta[0] = text_a[b].to(dev)
+            tb = torch.zeros(C + 1, 64, dtype=torch.int32, device=dev)
+            tb[0] = text_b[b].to(dev)
+            prompts.append(torch.cat([ta, vq, tb], dim=1))
+        outs = generate_batch(model=model, prompts=prompts, max_new_tokens=NF, temperature=0.7, top_p=0.7, top_k=1, seed=1)
+        gen = torch.stack([o[1:, p.shape[1]: p.shape[1] + NF] for o, p in zip(outs, prompts)]).contiguous()
+        return dac.from_indices(gen).cpu(), prompts[0].shape[1]
+
+    for _ in range(max(1, args.warmup)):
+        wav, plen = step()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        wav, plen = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    audio_s = B * NF * FRAME / SR
+    v = audio_s / (ms / 1e3)
+    print(json.dumps({
+        "metric": "audio-sec/s", "value": v, "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"voice-clone: batch-{B}, {REF_S} s reference audio -> encode -> {plen}-position prefill -> "
+                               f"{NF} frames -> waveform, S2-Pro geometry", "frames_per_s": B * NF / (ms / 1e3),
+                   "stages": ["codec_encode", "lm_prefill", "lm_decode", "codec_decode"]},
+        "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": audio_host.numel() * 4,
+                "d2h_bytes_per_step": wav.numel() * 4},
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,6 +267,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-codec", action="store_true", help="time the LM stages only")
     ap.add_argument("--profile-only", action="store_true", help="run the timed step once and exit (for ncu)")
+    ap.add_argument("--workload", default="batch32", choices=["batch32", "voice-clone"],
+                    help="batch32 = BASELINE configs[2] (the headline); voice-clone = configs[4]: 10 s reference "
+                         "audio -> codec encode -> ~350-position prefill -> 512 frames -> waveform, batch 8")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -205,6 +278,8 @@ def main():
     workload = (f"batch-{args.batch} text->codec->wav, {T_PROMPT}-token prompts, {args.frames} codec frames/utt, "
                 "S2-Pro 4B Dual-AR + 391M DAC codec geometry")
 
+    if args.workload == "voice-clone" and args.impl != "reference":
+        return voice_clone_bench(args)
     if args.impl == "reference":
         if rank != 0:
             return

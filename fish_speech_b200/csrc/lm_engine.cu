@@ -77,7 +77,7 @@ struct fsb_lm {
     float *slow_logits = nullptr, *fast_logits = nullptr;
     bf16* dbg_x = nullptr;
     bool persistent = false;
-    bool fused_prep_attn = true;
+    bool fused_prep_attn = false;
     int pk_stages = 8;
     unsigned* pk_bar = nullptr;
     unsigned long long* pk_trace = nullptr;
@@ -575,7 +575,7 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     }
     {
         const char* ef = getenv("FSB_FUSED_ATTN");
-        h->fused_prep_attn = !(ef && ef[0] == '0');
+        h->fused_prep_attn = ef && ef[0] == '1';  // measured slower than qkv_prep + attn (6.45 vs 6.22 ms/frame): off
         TRYC(pk_init());
     }
     if (h->persistent) {
