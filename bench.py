@@ -214,9 +214,10 @@ def voice_clone_bench(args):
     text_a = [torch.randint(0, 151643, (64,), generator=g, dtype=torch.int32) for _ in range(B)]
     text_b = [torch.randint(0, 151643, (64,), generator=g, dtype=torch.int32) for _ in range(B)]
     C = cfg.num_codebooks
+    audio_lens = torch.full((B,), 44100 * REF_S, dtype=torch.long, device=dev)
 
     def step():
-        codes, lens = dac.encode(audio_host.to(dev, non_blocking=True))  # [B, 10, 216]
+        codes, lens = dac.encode(audio_host.to(dev, non_blocking=True), audio_lens)  # [B, 10, 216]
         prompts = []
         for b in range(B):
             T = int(lens[b])
