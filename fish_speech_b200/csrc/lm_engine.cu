@@ -76,6 +76,8 @@ struct fsb_lm {
     // debug
     float *slow_logits = nullptr, *fast_logits = nullptr;
     bf16* dbg_x = nullptr;
+    int ctx_lcap = 0;  // score-buffer bound for the slow attention (0 = capacity)
+    int graph_lcap = -1;
     bool persistent = false;
     bool fused_prep_attn = false;
     int pk_stages = 8;
@@ -266,6 +268,7 @@ int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool
         aa.out = c.attn;
         aa.rows = c.rows; aa.H = s.H; aa.Hkv = s.Hkv; aa.Dh = s.Dh; aa.S = s.S;
         aa.window = 0;
+        aa.lcap = (s.bf16_math == 0) ? h->ctx_lcap : 0;  // slow stack: bounded by the live context, not the capacity
         aa.bf16_math = s.bf16_math;
         FSB_TRY(launch_attn(aa, st));
         }
@@ -705,7 +708,7 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int
         for (int i = 0; i < nframes; ++i) FSB_TRY(decode_one_frame(h, batch, *sp, st));
         return 0;
     }
-    const bool same = h->graph_exec && h->graph_batch == batch &&
+    const bool same = h->graph_exec && h->graph_batch == batch && h->graph_lcap == h->ctx_lcap &&
                       memcmp(&h->graph_sampling, sp, sizeof(fsb_sampling)) == 0;
     if (!same) {
         if (h->graph_exec) {
@@ -744,6 +747,7 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int
         }
         h->graph_exec = ge;
         h->graph_batch = batch;
+        h->graph_lcap = h->ctx_lcap;
         h->graph_sampling = *sp;
     }
     for (int i = 0; i < nframes; ++i) {
@@ -810,6 +814,17 @@ int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* l
     }
     if (weight_bytes_per_rep) *weight_bytes_per_rep = bytes;
     if (launches_per_rep) *launches_per_rep = launches;
+    return 0;
+}
+
+int fsb_lm_set_context_bound(fsb_lm* h, int max_positions) {
+    // The attention kernel keeps one fp32 score per live position in shared memory; sizing that buffer by
+    // the KV capacity would cap max_seq_len at ~12k. The host knows an upper bound of every slot's length
+    // (prompt + frames so far): round it up to a 1024 bucket (the decode graph is re-captured per bucket).
+    FSB_CHECK(max_positions >= 0, "set_context_bound: negative bound");
+    int b = ((max_positions + 1023) / 1024) * 1024;
+    if (b > h->cfg.kv_len) b = h->cfg.kv_len;
+    h->ctx_lcap = b;
     return 0;
 }
 

@@ -560,6 +560,7 @@ int launch_qkv_prep(const QkvPrepArgs& a, cudaStream_t st) {
 template <int DH, int G>
 static int launch_attn_t(const AttnArgs& a, cudaStream_t st) {
     int lcap = a.window > 0 && a.window < a.S ? a.window : a.S;
+    if (a.lcap > 0 && a.lcap < lcap) lcap = a.lcap;
     const size_t smem = (static_cast<size_t>(G) * DH + static_cast<size_t>(G) * lcap +
                          static_cast<size_t>(kAttnWarps) * G * DH) * sizeof(float);
     FSB_CHECK(smem <= 200 * 1024, "attention: context %d too long for the shared-memory score buffer", lcap);

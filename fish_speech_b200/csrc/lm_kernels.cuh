@@ -142,6 +142,7 @@ struct AttnArgs {
     __nv_bfloat16* out;  // [rows, H*Dh]
     int rows, H, Hkv, Dh, S;
     int window;  // <=0: unlimited
+    int lcap;    // score-buffer length: an upper bound of (row_pos + 1); 0 = cache capacity S
     int bf16_math;
 };
 int launch_attn(const AttnArgs& a, cudaStream_t st);

@@ -127,6 +127,7 @@ class LmEngine:
         self.h = h
         self.debug = debug
         self._views = {}
+        self._ctx_bound = 0  # upper bound of every slot's length, tracked on the host
 
     def close(self):
         if getattr(self, "h", None):
@@ -177,7 +178,18 @@ class LmEngine:
         s.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         return s
 
+    def _grow_bound(self, n: int):
+        n = min(int(n), self.kv_len)
+        if n > self._ctx_bound:
+            self._ctx_bound = n
+        _lib.check(self.lib.fsb_lm_set_context_bound(self.h, self._ctx_bound))
+
+    def set_context_bound(self, n: int):
+        """For callers that place tokens at explicit positions (decode_one_token_ar / decode_n_tokens)."""
+        self._grow_bound(n)
+
     def reset(self):
+        self._ctx_bound = 0
         with torch.cuda.device(self.device):
             _lib.check(self.lib.fsb_lm_reset(self.h, _stream()))
 
@@ -210,6 +222,7 @@ class LmEngine:
         if cur:
             groups.append(cur)
         dev = self.device
+        self._grow_bound(max(s0 + p.shape[1] for p, s0 in zip(prompts, start_pos)) + 1)
         with torch.cuda.device(dev):
             for grp in groups:
                 toks, rslot, rpos, last, gsl = [], [], [], [], []
@@ -240,5 +253,6 @@ class LmEngine:
 
         if os.environ.get("FSB_NO_GRAPH") == "1":  # diagnostic: eager launches instead of graph replays
             use_graph = False
+        self._grow_bound(self._ctx_bound + nframes)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.fsb_lm_decode(self.h, batch, nframes, C.byref(sp), int(use_graph), _stream()))

@@ -79,6 +79,7 @@ def decode_one_token_ar(
     else:
         eng.buffer("cur_tok")[0].copy_(x[0, :, 0].to(torch.int32))
         eng.buffer("pos")[0:1].copy_(input_pos.to(torch.int32).view(1))
+        eng.set_context_bound(int(input_pos.view(-1)[0].item()) + 1)
         win = eng.buffer("ras_window")
         if previous_tokens is not None:
             win[0].copy_(previous_tokens[0].to(torch.int32))
@@ -113,7 +114,9 @@ def decode_n_tokens(
     eng.buffer("n_out").zero_()
     eng.buffer("finished").zero_()
     eng.buffer("ras_window").zero_()
-    num_new_tokens = min(int(num_new_tokens), eng.max_frames)
+    start = int(input_pos.view(-1)[0].item())
+    eng.set_context_bound(start + 1)
+    num_new_tokens = min(int(num_new_tokens), eng.max_frames, eng.kv_len - start)  # never write past the KV cache
     n = _run_frames(eng, 1, num_new_tokens, sp, first_frame_from_prefill=False)[0]
     return eng.buffer("out_tokens")[0, :, :n].clone()
 

@@ -119,6 +119,10 @@ int fsb_lm_prefill(fsb_lm* h, const int32_t* d_tokens, const int32_t* d_row_slot
 int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* s, int use_graph,
                   void* stream);
 
+/* Upper bound of (position + 1) over all slots for the calls that follow (prompt length + frames decoded so
+ * far). Sizes the attention score buffer; must be set before prefill / decode whenever it grows. */
+int fsb_lm_set_context_bound(fsb_lm* h, int max_positions);
+
 /* Reset per-slot generation state (frame counters, RAS window, finished flags). */
 int fsb_lm_reset(fsb_lm* h, void* stream);
 

@@ -169,3 +169,16 @@ def test_stochastic_sampling_distribution():
     support = probs > 0
     assert freq[~support].sum().item() == 0, "sampled a token outside the top-k/top-p support"
     assert (freq - probs).abs().max().item() < 0.08, (freq[support], probs[support])
+
+
+def test_large_kv_capacity_small_context():
+    """A checkpoint-sized max_seq_len (32768, the S2-Pro config value) must not size the attention score
+    buffer: it follows the live context bound tracked by the host."""
+    cfg = O.tiny_config(max_seq_len=32768)
+    w = O.make_weights(cfg, seed=81, head_gain=8.0)
+    p = make_prompt(cfg, 81, 20)
+    ref_cfg = O.tiny_config(max_seq_len=128)  # same weights / tables for the positions touched
+    traces = []
+    ref = O.generate(O.setup(ref_cfg, w), p, 6, temperature=0.7, top_p=0.7, top_k=1, traces=traces, noise=False)
+    got = _gen(build_model(cfg, w), p, 6, temperature=0.7, top_p=0.7, top_k=1)
+    assert assert_tokens_match(got, ref, traces, ref_cfg, 20, "kv capacity 32768") >= 4
