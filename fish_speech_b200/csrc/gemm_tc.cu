@@ -255,7 +255,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
-            pdl_wait();
+            if (p.b_ready.ctr != nullptr) {
+                flag_wait(p.b_ready);
+                asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores of another grid -> TMA reads
+            } else {
+                pdl_wait();
+            }
             if (trace) trace[1] = globaltimer_ns();
             waited = true;
             (void)waited;
@@ -355,6 +360,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8u * a);
+        }
+        if (MODE == 0 && p.done_ctr != nullptr) {
+            // publish this CTA's partial sums: every epilogue thread fences its stores, the epilogue warps
+            // meet on a named barrier, one thread does the release increment
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(GemmRoles<MODE>::kEpiWarps * 32) : "memory");
+            if (threadIdx.x == 0) red_release_gpu(p.done_ctr);
         }
     }
     tc_fence_before();

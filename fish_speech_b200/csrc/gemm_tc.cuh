@@ -31,6 +31,8 @@ struct GemmParams {
     int stages;
     int a_static;  // operand A is constant data (weights): prefetch it before griddepcontrol.wait
     int l2_prefetch;  // extra k-blocks of A per CTA prefetched into L2 before the wait
+    DepFlag b_ready;     // optional: activations (operand B) are published by this flag instead of grid completion
+    unsigned* done_ctr;  // optional: incremented once per CTA when its partials are written (MODE 0)
     unsigned long long* trace;  // optional [launch][cta][3] globaltimer: start, after dependency wait, end
     int trace_id;
     // ---- work decomposition ----

@@ -54,6 +54,11 @@ struct Stack {
 }  // namespace
 
 struct fsb_lm {
+    // device-side dependency flags for the decode chain (FSB_FLAGS, see common.cuh DepFlag)
+    bool flags_on = false;
+    unsigned* flag_base = nullptr;
+    int flag_next = 0;
+    static constexpr int kFlagCap = 4096;
     fsb_lm_config cfg;
     int num_sms = 148;
     Stack slow, fast;
@@ -160,6 +165,30 @@ Partials parts_of(const GemmPlan& p) {
     return P;
 }
 
+// Every frame starts from zeroed counters; each dependency edge of the frame gets its own counter.
+int flags_begin(fsb_lm* h, cudaStream_t st) {
+    if (!h->flags_on) return 0;
+    h->flag_next = 0;
+    FSB_CUDA(cudaMemsetAsync(h->flag_base, 0, static_cast<size_t>(fsb_lm::kFlagCap) * 4, st));
+    return 0;
+}
+unsigned* flag_new(fsb_lm* h) {
+    if (!h->flags_on || h->flag_next >= fsb_lm::kFlagCap) return nullptr;
+    return h->flag_base + h->flag_next++;
+}
+
+// Decode GEMM with flag dependencies: operand B becomes valid when `ready` is satisfied; the returned
+// flag is satisfied when every CTA has written its partial sums.
+int launch_dec_gemm(fsb_lm* h, const GemmPlan& plan, const DepFlag& ready, DepFlag* done, cudaStream_t st) {
+    *done = DepFlag{nullptr, 0};
+    if (!h->flags_on) return gemm_launch(plan, st);
+    GemmPlan q = plan;
+    q.p.b_ready = ready;
+    q.p.done_ctr = flag_new(h);
+    if (q.p.done_ctr) *done = DepFlag{q.p.done_ctr, plan.grid.x * plan.grid.y * plan.grid.z};
+    return gemm_launch(q, st);
+}
+
 int launch_rows(const GemmPlan& plan, int rows, cudaStream_t st) {
     // prefill plans: restrict the column tiles to the live rows
     if (plan.p.sched == nullptr) {
@@ -183,8 +212,12 @@ struct RowCtx {
 // `final_norm`: weight of the norm applied after the last layer (-> xn). `stop_after_kv`: fast pass 0
 // only needs the last layer's K/V (its logits are discarded, inference.py:147).
 int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool stop_after_kv,
-              bf16* dbg, cudaStream_t st) {
+              bf16* dbg, cudaStream_t st, DepFlag* ready_io = nullptr) {
     const float eps = h->cfg.norm_eps;
+    // flag mode (decode only): `ready` = "xn holds this layer's normed input"
+    const bool fl = h->flags_on && c.decode && ready_io != nullptr && !h->persistent && !h->fused_prep_attn;
+    DepFlag ready = fl ? *ready_io : DepFlag{nullptr, 0};
+    DepFlag gd{nullptr, 0};
     if (h->persistent && c.decode && s.pk_layers != nullptr) {
         PkArgs A{};
         A.layers = s.pk_layers;
@@ -212,7 +245,8 @@ int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool
     for (int l = 0; l < s.nl; ++l) {
         const LayerW& w = s.w[l];
         LayerPlans& P = c.decode ? s.dec[l] : s.pf[l];
-        FSB_TRY(launch_rows(P.qkv, c.rows, st));
+        if (fl) FSB_TRY(launch_dec_gemm(h, P.qkv, ready, &gd, st));
+        else FSB_TRY(launch_rows(P.qkv, c.rows, st));
         if (c.decode && h->fused_prep_attn) {
             // decode rows: q/k/v post-processing, KV append and attention in one launch
             PkArgs A{};
@@ -257,8 +291,12 @@ int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool
         qa.vcache = s.vcache + l * s.cache_layer_stride;
         qa.rows = c.rows; qa.H = s.H; qa.Hkv = s.Hkv; qa.Dh = s.Dh; qa.S = s.S;
         qa.eps = eps;
+        qa.wait = gd;
         FSB_TRY(launch_qkv_prep(qa, st));
-        if (stop_after_kv && l == s.nl - 1) return 0;
+        if (stop_after_kv && l == s.nl - 1) {
+            if (ready_io) *ready_io = DepFlag{nullptr, 0};  // the next kernel depends on this grid classically
+            return 0;
+        }
         AttnArgs aa{};
         aa.q = c.q;
         aa.kcache = qa.kcache;
@@ -270,48 +308,66 @@ int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool
         aa.window = 0;
         aa.lcap = (s.bf16_math == 0) ? h->ctx_lcap : 0;  // slow stack: bounded by the live context, not the capacity
         aa.bf16_math = s.bf16_math;
+        aa.done_ctr = fl ? flag_new(h) : nullptr;
         FSB_TRY(launch_attn(aa, st));
+        ready = DepFlag{aa.done_ctr, static_cast<unsigned>(s.Hkv * c.rows)};
         }
     after_attention:
-        FSB_TRY(launch_rows(P.wo, c.rows, st));
+        if (fl) FSB_TRY(launch_dec_gemm(h, P.wo, ready, &gd, st));
+        else FSB_TRY(launch_rows(P.wo, c.rows, st));
         ResidNormArgs r1{};
         r1.parts = parts_of(P.wo);
         r1.bias = w.bo;
         r1.x_in = c.xres; r1.x_out = c.xres;
         r1.norm_w = w.ffn_norm; r1.n_out = c.xn;
         r1.rows = c.rows; r1.D = s.D; r1.eps = eps;
+        r1.wait = gd;
+        r1.done_ctr = fl ? flag_new(h) : nullptr;
         FSB_TRY(launch_resid_norm(r1, st));
-        FSB_TRY(launch_rows(P.w13, c.rows, st));
+        ready = DepFlag{r1.done_ctr, static_cast<unsigned>(c.rows)};
+        if (fl) FSB_TRY(launch_dec_gemm(h, P.w13, ready, &gd, st));
+        else FSB_TRY(launch_rows(P.w13, c.rows, st));
         SwigluArgs sa{};
         sa.parts = parts_of(P.w13);
         sa.h = c.hbuf; sa.rows = c.rows; sa.I = s.I;
+        sa.wait = gd;
+        sa.done_ctr = fl ? flag_new(h) : nullptr;
         FSB_TRY(launch_swiglu(sa, st));
-        FSB_TRY(launch_rows(P.w2, c.rows, st));
+        ready = DepFlag{sa.done_ctr, static_cast<unsigned>(cdiv(s.I, 256) * c.rows)};
+        if (fl) FSB_TRY(launch_dec_gemm(h, P.w2, ready, &gd, st));
+        else FSB_TRY(launch_rows(P.w2, c.rows, st));
         ResidNormArgs r2{};
         r2.parts = parts_of(P.w2);
         r2.x_in = c.xres; r2.x_out = c.xres;
         r2.norm_w = (l + 1 < s.nl) ? s.w[l + 1].attn_norm : final_norm;
         r2.n_out = c.xn;
         r2.rows = c.rows; r2.D = s.D; r2.eps = eps;
+        r2.wait = gd;
+        r2.done_ctr = fl ? flag_new(h) : nullptr;
         FSB_TRY(launch_resid_norm(r2, st));
+        ready = DepFlag{r2.done_ctr, static_cast<unsigned>(c.rows)};
         if (dbg)
             FSB_CUDA(cudaMemcpyAsync(dbg + static_cast<size_t>(l + 1) * kDecRows * s.D, c.xres,
                                      static_cast<size_t>(std::min(c.rows, kDecRows)) * s.D * 2,
                                      cudaMemcpyDeviceToDevice, st));
     }
+    if (ready_io) *ready_io = ready;
     return 0;
 }
 
 // Head + sampling + fast passes + bookkeeping for `rows` sequences whose final-normed last hidden
 // state is in xn_d[0..rows) (and un-normed residual in xres_d). inference.py:114-181.
 int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const int* set_pos_rows,
-                   const int* row_pos_src, const fsb_sampling& sp, cudaStream_t st) {
+                   const int* row_pos_src, const fsb_sampling& sp, cudaStream_t st,
+                   DepFlag ready = DepFlag{nullptr, 0}) {
     const fsb_lm_config& c = h->cfg;
     const int C = c.num_codebooks;
     const int* slots = row_slot ? row_slot : h->iota;
     // ---- slow head over the selectable rows ----
-    FSB_TRY(gemm_launch(h->head_plan, st));
+    DepFlag gd{nullptr, 0};
+    FSB_TRY(launch_dec_gemm(h, h->head_plan, ready, &gd, st));
     SampleArgs sa{};
+    sa.wait = gd;
     sa.parts = parts_of(h->head_plan);
     sa.n = h->head_rows;
     sa.rows = rows;
@@ -363,18 +419,22 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
             } else {
                 r.x_in = hidden;
             }
+            r.done_ctr = flag_new(h);
             FSB_TRY(launch_resid_norm(r, st));
         } else {
             // input = fast_embeddings[code_{p-1}] ; codes live in cur_tok[slot][p]
             r.x_in = h->fast_emb;
             r.gather = h->cur_tok + p;
             r.gather_map = row_slot;
+            r.done_ctr = flag_new(h);
             FSB_TRY(launch_resid_norm_g(r, C + 1, st));
         }
-        FSB_TRY(run_stack(h, f, ctx, h->fast_norm_w, p == 0, nullptr, st));
+        DepFlag fr{r.done_ctr, static_cast<unsigned>(rows)};
+        FSB_TRY(run_stack(h, f, ctx, h->fast_norm_w, p == 0, nullptr, st, &fr));
         if (p == 0) continue;
-        FSB_TRY(gemm_launch(h->fast_out_plan, st));
+        FSB_TRY(launch_dec_gemm(h, h->fast_out_plan, fr, &gd, st));
         SampleArgs fa{};
+        fa.wait = gd;
         fa.parts = parts_of(h->fast_out_plan);
         fa.n = c.codebook_size;
         fa.rows = rows;
@@ -414,19 +474,22 @@ int decode_one_frame(fsb_lm* h, int batch, const fsb_sampling& sp, cudaStream_t 
     ea.rows = batch; ea.D = s.D; ea.C = c.num_codebooks; ea.cs = c.codebook_size; ea.vocab = c.vocab_size;
     ea.sem_begin = c.semantic_begin_id; ea.sem_end = c.semantic_end_id;
     ea.scale = c.scale_codebook_embeddings;
+    FSB_TRY(flags_begin(h, st));
     FSB_TRY(launch_embed(ea, st));
     ResidNormArgs r{};
     r.x_in = h->xres_d;
     r.norm_w = s.w[0].attn_norm; r.n_out = h->xn_d;
     r.rows = batch; r.D = s.D; r.eps = c.norm_eps;
+    r.done_ctr = flag_new(h);
     FSB_TRY(launch_resid_norm(r, st));
+    DepFlag ready{r.done_ctr, static_cast<unsigned>(batch)};
     bf16* dbg = (h->dbg_x && h->graph_exec == nullptr) ? h->dbg_x : nullptr;
     if (dbg)
         FSB_CUDA(cudaMemcpyAsync(dbg, h->xres_d, static_cast<size_t>(batch) * s.D * 2,
                                  cudaMemcpyDeviceToDevice, st));
     RowCtx ctx{batch, h->iota, h->pos, h->xres_d, h->xn_d, h->q_d, h->attn_d, h->h_d, true};
-    FSB_TRY(run_stack(h, s, ctx, h->norm_w, false, dbg, st));
-    return run_frame_tail(h, batch, nullptr, true, nullptr, nullptr, sp, st);
+    FSB_TRY(run_stack(h, s, ctx, h->norm_w, false, dbg, st, &ready));
+    return run_frame_tail(h, batch, nullptr, true, nullptr, nullptr, sp, st, ready);
 }
 
 }  // namespace
@@ -531,6 +594,11 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     TRYC(dalloc(h, &h->iota, kDecRows));
     TRYC(dalloc(h, &h->fpos, static_cast<size_t>(C) * kDecRows));
     TRYC(dalloc(h, &h->step, 1));
+    {
+        const char* ef = getenv("FSB_FLAGS");
+        h->flags_on = ef && ef[0] == '1';
+        if (h->flags_on) TRYC(dalloc(h, &h->flag_base, static_cast<size_t>(fsb_lm::kFlagCap)));
+    }
     if (cfg->debug) {
         TRYC(dalloc(h, &h->slow_logits, static_cast<size_t>(cfg->max_batch) * h->head_rows, "slow_logits"));
         TRYC(dalloc(h, &h->fast_logits, static_cast<size_t>(C) * cfg->max_batch * cfg->codebook_size, "fast_logits"));
@@ -692,6 +760,7 @@ int fsb_lm_prefill(fsb_lm* h, const int32_t* d_tokens, const int32_t* d_row_slot
     FSB_TRY(launch_gather_rows(h->xn_p, d_last_rows, h->xn_d, nseq, s.D, st));
     FSB_TRY(launch_gather_rows(h->xres_p, d_last_rows, h->xres_d, nseq, s.D, st));
     // the reference resets the RAS window per generate() call and prefill uses no RAS
+    FSB_TRY(flags_begin(h, st));
     return run_frame_tail(h, nseq, d_slots, false, d_last_rows, d_row_pos, *sp, st);
 }
 

@@ -40,7 +40,7 @@ constexpr int kRnMaxPer = 8;  // D <= 4096
 
 __global__ void __launch_bounds__(kRnThreads) resid_norm_kernel(ResidNormArgs a, int gstride) {
     pdl_launch_dependents();
-    pdl_wait();
+    dep_wait_cta(a.wait);
     __shared__ float red[33];
     const int row = blockIdx.x;
     const int grow = a.gather_map ? a.gather_map[row] : row;
@@ -74,16 +74,18 @@ __global__ void __launch_bounds__(kRnThreads) resid_norm_kernel(ResidNormArgs a,
             if (a.x_out) a.x_out[static_cast<size_t>(row) * a.D + fts[e]] = f2bf(x);
         }
     }
-    if (a.norm_w == nullptr) return;
-    const float tot = block_sum(ss, red);
-    const float r = rsqrtf(tot / static_cast<float>(a.D) + a.eps);
+    if (a.norm_w != nullptr) {
+        const float tot = block_sum(ss, red);
+        const float r = rsqrtf(tot / static_cast<float>(a.D) + a.eps);
 #pragma unroll
-    for (int e = 0; e < kRnMaxPer; ++e) {
-        if (ok[e]) {
-            const float n = rbf(rbf(v[e] * r) * bf2f(a.norm_w[fts[e]]));
-            a.n_out[static_cast<size_t>(row) * a.D + fts[e]] = f2bf(n);
+        for (int e = 0; e < kRnMaxPer; ++e) {
+            if (ok[e]) {
+                const float n = rbf(rbf(v[e] * r) * bf2f(a.norm_w[fts[e]]));
+                a.n_out[static_cast<size_t>(row) * a.D + fts[e]] = f2bf(n);
+            }
         }
     }
+    dep_signal_cta(a.done_ctr);
 }
 
 __global__ void linear_out_kernel(LinearOutArgs a) {
@@ -102,7 +104,7 @@ __global__ void linear_out_kernel(LinearOutArgs a) {
 // ------------------------------------------------------------------------------------------------
 __global__ void qkv_prep_kernel(QkvPrepArgs a) {
     pdl_launch_dependents();
-    pdl_wait();
+    dep_wait_cta(a.wait);
     __shared__ float red[33];
     const int row = blockIdx.x, head = blockIdx.y;
     const int t = threadIdx.x;  // pair index, Dh/2 threads
@@ -292,21 +294,24 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnArgs a, float sc
         const int gg = e / DH, d = e - gg * DH;
         a.out[(static_cast<size_t>(row) * a.H + g * G + gg) * DH + d] = f2bf(s);
     }
+    dep_signal_cta(a.done_ctr);
 }
 
 __global__ void swiglu_kernel(SwigluArgs a) {
     pdl_launch_dependents();
-    pdl_wait();
+    dep_wait_cta(a.wait);
     const int row = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.I) return;
-    const int rws[2] = {row, row}, fts[2] = {i, a.I + i};
-    const bool ok[2] = {true, true};
-    float y[2];
-    sum_parts_n<2>(a.parts, rws, fts, ok, y, a.parts.max_parts > 0 ? a.parts.max_parts : 1);
-    const float g = rbf(y[0]), c = rbf(y[1]);
-    const float s = rbf(g / (1.f + expf(-g)));
-    a.h[static_cast<size_t>(row) * a.I + i] = f2bf(s * c);
+    if (i < a.I) {
+        const int rws[2] = {row, row}, fts[2] = {i, a.I + i};
+        const bool ok[2] = {true, true};
+        float y[2];
+        sum_parts_n<2>(a.parts, rws, fts, ok, y, a.parts.max_parts > 0 ? a.parts.max_parts : 1);
+        const float g = rbf(y[0]), c = rbf(y[1]);
+        const float s = rbf(g / (1.f + expf(-g)));
+        a.h[static_cast<size_t>(row) * a.I + i] = f2bf(s * c);
+    }
+    dep_signal_cta(a.done_ctr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -369,7 +374,7 @@ __device__ __forceinline__ ArgMax block_argmax(ArgMax x, ArgMax* red) {
 
 __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
     pdl_launch_dependents();
-    pdl_wait();
+    dep_wait_cta(a.wait);
     __shared__ float lg[kSampleMaxN];
     __shared__ ArgMax red[33];
     __shared__ float fred[33];

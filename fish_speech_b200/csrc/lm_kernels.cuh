@@ -87,6 +87,8 @@ int launch_embed(const EmbedArgs& a, cudaStream_t st);
 // x_out = rbf(x_in + rbf(sum partials + bias))   (skip the add when parts.ws == null)
 // n_out = rbf(rbf(x_out * rsqrt(mean(x_out^2)+eps)) * w)     [fish RMSNorm: round, then * weight]
 struct ResidNormArgs {
+    DepFlag wait;        // optional flag dependency (else grid dependency)
+    unsigned* done_ctr;  // optional: signalled once per CTA at the end
     Partials parts;
     const __nv_bfloat16* bias;  // [D] or null (attention_o_bias)
     const __nv_bfloat16* scale;  // [D] or null: y *= scale (codec LayerScale, modded_dac.py:329-341)
@@ -115,6 +117,7 @@ int launch_linear_out(const LinearOutArgs& a, cudaStream_t st);
 // q,k,v = rbf(partials [+bias]); optional per-head nn.RMSNorm (single rounding); interleaved RoPE in
 // fp32 with bf16 tables; q -> qbuf[row][H][Dh]; k,v -> cache[b][hkv][pos][Dh].
 struct QkvPrepArgs {
+    DepFlag wait;
     Partials parts;
     const __nv_bfloat16* bias;  // [(H+2Hkv)*Dh] or null
     const __nv_bfloat16* q_norm;  // [Dh] or null
@@ -134,6 +137,7 @@ int launch_qkv_prep(const QkvPrepArgs& a, cudaStream_t st);
 // bf16_math = 1 reproduces the fast-AR hand-rolled attention (llama.py:948-976): scores, scaled
 // scores, probabilities and the output are each rounded to bf16.
 struct AttnArgs {
+    unsigned* done_ctr;  // optional: signalled once per CTA at the end
     const __nv_bfloat16* q;  // [rows, H, Dh]
     const __nv_bfloat16* kcache;
     const __nv_bfloat16* vcache;
@@ -150,6 +154,8 @@ int attn_init();  // set kernel attributes (idempotent)
 
 // h = rbf( rbf(silu(rbf(a))) * rbf(c) ), a = feature i, c = feature I+i of the fused w1|w3 GEMM
 struct SwigluArgs {
+    DepFlag wait;
+    unsigned* done_ctr;
     Partials parts;
     __nv_bfloat16* h;  // [rows, I]
     int rows, I;
@@ -157,6 +163,7 @@ struct SwigluArgs {
 int launch_swiglu(const SwigluArgs& a, cudaStream_t st);
 
 struct SampleArgs {
+    DepFlag wait;
     Partials parts;  // logits of the (restricted) head: n entries per row
     int n;           // number of candidate entries (<= 8192)
     int rows;

@@ -41,6 +41,18 @@ def test_greedy_tokens_match_reference_golden(name):
     assert torch.equal(got.to(torch.int32), ref), f"first mismatch at {(got != ref).nonzero()[:4].tolist()}"
 
 
+@pytest.mark.parametrize("flag", ["FSB_FLAGS", "FSB_PERSISTENT", "FSB_FUSED_ATTN"])
+def test_optin_decode_variants_match_reference_golden(flag, monkeypatch):
+    """The opt-in decode-chain experiments (device-side dependency flags, persistent stack kernel, fused
+    prep+attention) must produce the reference's tokens too."""
+    monkeypatch.setenv(flag, "1")
+    cfg, w, z = load_golden(GOLD / "lm_tiny_greedy.npz")
+    model = build_model(cfg, w)
+    got = _gen(model, torch.from_numpy(z["prompt"]), int(z["new_frames"]), temperature=float(z["temperature"]),
+               top_p=float(z["top_p"]), top_k=int(z["top_k"]))
+    assert torch.equal(got.to(torch.int32), torch.from_numpy(z["ref_tokens"]))
+
+
 def test_prefill_and_decode_logits_teacher_forced():
     """Per-frame slow/fast logits vs the oracle with the oracle's own tokens fed back (teacher forcing)."""
     from fish_speech_b200.models.text2semantic.inference import decode_one_token_ar
