@@ -257,6 +257,81 @@ def voice_clone_bench(args):
     }))
 
 
+def serve_bench(args):
+    """a queue of requests with RAGGED lengths (the fixed-length headline hides what the
+    reference's one-request-at-a-time worker and a static batch both lose). 96 requests, 64-token prompts,
+    64..256 frames each (seeded), greedy, LM stage only (the codec stage is the same work either way).
+    Measured twice on the same requests: static batches of 32 in arrival order (`generate_batch`: a batch
+    lasts as long as its longest request) and the slot scheduler (`ContinuousBatcher`, 32 slots)."""
+    from fish_speech_b200 import synthetic
+    from fish_speech_b200.configs import S2PRO_IM_END_ID, s2pro_args
+    from fish_speech_b200.models.text2semantic.inference import generate_batch
+    from fish_speech_b200.models.text2semantic.llama import DualARTransformer
+    from fish_speech_b200.scheduler import ContinuousBatcher, SlotRequest
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    NREQ, SLOTS = 96, 32
+    cfg = s2pro_args(max_seq_len=T_PROMPT + 256)
+    w = synthetic.lm_state_dict(cfg, dev)
+    w["embeddings.weight"][S2PRO_IM_END_ID] = 0  # lengths are set by the per-request budgets
+    model = DualARTransformer(cfg, w, device=dev, im_end_id=S2PRO_IM_END_ID)
+    model.max_rows = SLOTS * T_PROMPT
+    model.setup_caches(max_batch_size=SLOTS, max_seq_len=cfg.max_seq_len)
+    del w
+    g = torch.Generator().manual_seed(7)
+    lens = torch.randint(64, 257, (NREQ,), generator=g).tolist()
+    prompts = [p.to(dev) for p in make_prompts(cfg, NREQ, 42)]
+    audio_s = sum(lens) * FRAME / SR
+
+    def static():
+        outs = []
+        for i in range(0, NREQ, SLOTS):
+            n = max(lens[i:i + SLOTS])
+            o = generate_batch(model=model, prompts=prompts[i:i + SLOTS], max_new_tokens=n, temperature=0.7,
+                               top_p=0.7, top_k=1, seed=1)
+            outs += [x[:, :T_PROMPT + k] for x, k in zip(o, lens[i:i + SLOTS])]
+        return outs
+
+    stats = {}
+
+    def continuous():
+        b = ContinuousBatcher(model, max_slots=SLOTS, frames_per_poll=8)
+        reqs = [b.submit(SlotRequest(prompt=p, max_new_tokens=k, temperature=0.7, top_p=0.7, top_k=1, seed=1))
+                for p, k in zip(prompts, lens)]
+        b.run()
+        stats["frames_run"], stats["occupancy"] = b.frames_run, b.slot_frames / max(1, b.frames_run * SLOTS)
+        b.close()
+        return [r.result for r in reqs]
+
+    def timed(fn):
+        for _ in range(max(1, min(args.warmup, 2))):
+            out = fn()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.steps):
+            out = fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / args.steps, out
+
+    ms_s, out_s = timed(static)
+    ms_c, out_c = timed(continuous)
+    same = all(torch.equal(a, b) for a, b in zip(out_s, out_c))
+    v = audio_s / (ms_c / 1e3)
+    print(json.dumps({
+        "metric": "audio-sec/s", "value": v, "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_c, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"serve: {NREQ} queued requests, {T_PROMPT}-token prompts, 64..256 frames each "
+                               f"(mean {sum(lens) / NREQ:.0f}), greedy, LM stage only, {SLOTS} slots, S2-Pro geometry",
+                   "static_batches_audio_s_per_s": audio_s / (ms_s / 1e3), "static_ms": ms_s,
+                   "continuous_over_static": ms_s / ms_c, "slot_occupancy": stats["occupancy"],
+                   "decode_frames_run": stats["frames_run"], "identical_tokens": bool(same)},
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -268,7 +343,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-codec", action="store_true", help="time the LM stages only")
     ap.add_argument("--profile-only", action="store_true", help="run the timed step once and exit (for ncu)")
-    ap.add_argument("--workload", default="batch32", choices=["batch32", "voice-clone"],
+    ap.add_argument("--workload", default="batch32", choices=["batch32", "voice-clone", "serve"],
                     help="batch32 = BASELINE configs[2] (the headline); voice-clone = configs[4]: 10 s reference "
                          "audio -> codec encode -> ~350-position prefill -> 512 frames -> waveform, batch 8")
     args = ap.parse_args()
@@ -281,6 +356,8 @@ def main():
 
     if args.workload == "voice-clone" and args.impl != "reference":
         return voice_clone_bench(args)
+    if args.workload == "serve" and args.impl != "reference":
+        return serve_bench(args)
     if args.impl == "reference":
         if rank != 0:
             return

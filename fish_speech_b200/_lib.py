@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
     L.fsb_lm_decode.argtypes = [vp, i32, i32, C.POINTER(Sampling), i32, vp]
     L.fsb_lm_reset.argtypes = [vp, vp]
     L.fsb_lm_set_context_bound.argtypes = [vp, i32]
+    L.fsb_lm_set_slot_control.argtypes = [vp, i32]
     L.fsb_lm_buffer.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.fsb_lm_trace_gemms.argtypes = [vp, vp, i32, C.POINTER(i32), vp]
     L.fsb_lm_bench_gemms.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(i32), vp]

@@ -59,6 +59,15 @@ struct fsb_lm {
     unsigned* flag_base = nullptr;
     int flag_next = 0;
     static constexpr int kFlagCap = 4096;
+    // per-slot request control (continuous batching): see SlotCtl in lm_kernels.cuh
+    bool slot_control = false;
+    int* slot_state = nullptr;
+    int* slot_limit = nullptr;
+    float* slot_temperature = nullptr;
+    float* slot_top_p = nullptr;
+    int* slot_top_k = nullptr;
+    unsigned long long* slot_seed = nullptr;
+    bool graph_slot_control = false;
     fsb_lm_config cfg;
     int num_sms = 148;
     Stack slow, fast;
@@ -355,6 +364,19 @@ int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool
     return 0;
 }
 
+SlotCtl slot_ctl(const fsb_lm* h) {
+    SlotCtl c{};
+    if (!h->slot_control) return c;
+    c.state = h->slot_state;
+    c.limit = h->slot_limit;
+    c.temperature = h->slot_temperature;
+    c.top_p = h->slot_top_p;
+    c.top_k = h->slot_top_k;
+    c.seed = h->slot_seed;
+    c.n_out = h->n_out;
+    return c;
+}
+
 // Head + sampling + fast passes + bookkeeping for `rows` sequences whose final-normed last hidden
 // state is in xn_d[0..rows) (and un-normed residual in xres_d). inference.py:114-181.
 int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const int* set_pos_rows,
@@ -368,6 +390,7 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
     FSB_TRY(launch_dec_gemm(h, h->head_plan, ready, &gd, st));
     SampleArgs sa{};
     sa.wait = gd;
+    sa.ctl = slot_ctl(h);
     sa.parts = parts_of(h->head_plan);
     sa.n = h->head_rows;
     sa.rows = rows;
@@ -435,6 +458,7 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
         FSB_TRY(launch_dec_gemm(h, h->fast_out_plan, fr, &gd, st));
         SampleArgs fa{};
         fa.wait = gd;
+        fa.ctl = slot_ctl(h);
         fa.parts = parts_of(h->fast_out_plan);
         fa.n = c.codebook_size;
         fa.rows = rows;
@@ -452,6 +476,7 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
         FSB_TRY(launch_sample(fa, st));
     }
     FrameEndArgs fe{};
+    fe.ctl = slot_ctl(h);
     fe.cur_tok = h->cur_tok;
     fe.out_tokens = h->out_tokens;
     fe.n_out = h->n_out;
@@ -591,6 +616,12 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     TRYC(dalloc(h, &h->pos, kDecRows, "pos"));
     TRYC(dalloc(h, &h->finished, cfg->max_batch, "finished"));
     TRYC(dalloc(h, &h->ras_window, static_cast<size_t>(cfg->max_batch) * 10, "ras_window"));
+    TRYC(dalloc(h, &h->slot_state, cfg->max_batch, "slot_state"));
+    TRYC(dalloc(h, &h->slot_limit, cfg->max_batch, "slot_limit"));
+    TRYC(dalloc(h, &h->slot_temperature, cfg->max_batch, "slot_temperature"));
+    TRYC(dalloc(h, &h->slot_top_p, cfg->max_batch, "slot_top_p"));
+    TRYC(dalloc(h, &h->slot_top_k, cfg->max_batch, "slot_top_k"));
+    TRYC(dalloc(h, &h->slot_seed, cfg->max_batch, "slot_seed"));
     TRYC(dalloc(h, &h->iota, kDecRows));
     TRYC(dalloc(h, &h->fpos, static_cast<size_t>(C) * kDecRows));
     TRYC(dalloc(h, &h->step, 1));
@@ -726,6 +757,7 @@ int fsb_lm_reset(fsb_lm* h, void* stream) {
     const fsb_lm_config& c = h->cfg;
     FSB_CUDA(cudaMemsetAsync(h->n_out, 0, c.max_batch * 4, st));
     FSB_CUDA(cudaMemsetAsync(h->finished, 0, c.max_batch * 4, st));
+    FSB_CUDA(cudaMemsetAsync(h->slot_state, 0, c.max_batch * 4, st));
     FSB_CUDA(cudaMemsetAsync(h->ras_window, 0, static_cast<size_t>(c.max_batch) * 10 * 4, st));
     FSB_CUDA(cudaMemsetAsync(h->pos, 0, kDecRows * 4, st));
     FSB_CUDA(cudaMemsetAsync(h->step, 0, 8, st));
@@ -755,7 +787,9 @@ int fsb_lm_prefill(fsb_lm* h, const int32_t* d_tokens, const int32_t* d_row_slot
     RowCtx ctx{rows, d_row_slot, d_row_pos, h->xres_p, h->xn_p, h->q_p, h->attn_p, h->h_p, false};
     FSB_TRY(run_stack(h, s, ctx, h->norm_w, false, nullptr, st));
     if (!do_sample) return 0;
-    FSB_CHECK(sp != nullptr, "prefill: sampling parameters required");
+    FSB_CHECK(sp != nullptr || h->slot_control, "prefill: sampling parameters required");
+    const fsb_sampling sp_none{1.f, 1.f, 1, 0};
+    if (sp == nullptr) sp = &sp_none;
     // last-token rows -> decode workspaces (llama.py:447-448 keeps only the last position)
     FSB_TRY(launch_gather_rows(h->xn_p, d_last_rows, h->xn_d, nseq, s.D, st));
     FSB_TRY(launch_gather_rows(h->xres_p, d_last_rows, h->xres_d, nseq, s.D, st));
@@ -764,10 +798,18 @@ int fsb_lm_prefill(fsb_lm* h, const int32_t* d_tokens, const int32_t* d_row_slot
     return run_frame_tail(h, nseq, d_slots, false, d_last_rows, d_row_pos, *sp, st);
 }
 
+int fsb_lm_set_slot_control(fsb_lm* h, int enable) {
+    FSB_CHECK(h != nullptr, "set_slot_control: null handle");
+    h->slot_control = enable != 0;
+    return 0;
+}
+
 int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int use_graph, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     FSB_CHECK(batch >= 1 && batch <= h->cfg.max_batch, "decode: batch=%d out of range", batch);
-    FSB_CHECK(sp != nullptr, "decode: sampling parameters required");
+    FSB_CHECK(sp != nullptr || h->slot_control, "decode: sampling parameters required");
+    const fsb_sampling sp_none{1.f, 1.f, 1, 0};
+    if (sp == nullptr || h->slot_control) sp = &sp_none;  // per-slot parameters: one graph for every mix of requests
     if (!use_graph) {
         if (h->graph_exec) {  // debug copies are only recorded outside graphs
             cudaGraphExecDestroy(h->graph_exec);
@@ -778,6 +820,7 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int
         return 0;
     }
     const bool same = h->graph_exec && h->graph_batch == batch && h->graph_lcap == h->ctx_lcap &&
+                      h->graph_slot_control == h->slot_control &&
                       memcmp(&h->graph_sampling, sp, sizeof(fsb_sampling)) == 0;
     if (!same) {
         if (h->graph_exec) {
@@ -817,6 +860,7 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int
         h->graph_exec = ge;
         h->graph_batch = batch;
         h->graph_lcap = h->ctx_lcap;
+        h->graph_slot_control = h->slot_control;
         h->graph_sampling = *sp;
     }
     for (int i = 0; i < nframes; ++i) {

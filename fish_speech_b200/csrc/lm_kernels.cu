@@ -386,6 +386,12 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
     const int row = blockIdx.x;
     const int slot = a.row_slot ? a.row_slot[row] : row;
     const int n = a.n;
+    if (!slot_live(a.ctl, slot)) return;  // idle / frozen slot: nothing is sampled, its state stays as it is
+    const bool per_slot = a.ctl.state != nullptr;
+    const float temperature = per_slot ? a.ctl.temperature[slot] : a.temperature;
+    const float top_p = per_slot ? a.ctl.top_p[slot] : a.top_p;
+    const int top_k = per_slot ? a.ctl.top_k[slot] : a.top_k;
+    const unsigned long long seed = per_slot ? a.ctl.seed[slot] : a.seed;
     for (int e = threadIdx.x; e < n; e += kSampleThreads) {
         const float v = rbf(sum_parts(a.parts, row, e));
         lg[e] = v;
@@ -393,8 +399,8 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
     }
     __syncthreads();
 
-    const bool two = a.slow && a.use_ras && a.top_k != 1;
-    if (a.top_k == 1) {
+    const bool two = a.slow && a.use_ras && top_k != 1;
+    if (top_k == 1) {
         ArgMax x{-INFINITY, 0x7fffffff};
         for (int e = threadIdx.x; e < n; e += kSampleThreads) x = better(x, ArgMax{lg[e], e});
         x = block_argmax(x, red);
@@ -409,8 +415,8 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
         for (int e = threadIdx.x; e < n; e += kSampleThreads) z += expf(lg[e] - m);
         z = block_sum(z, fred);
         // descending ranks until neither criterion can keep anything further
-        const float p_lim = two ? fmaxf(a.top_p, 0.9f) : a.top_p;
-        int kcap = a.top_k < n ? a.top_k : n;
+        const float p_lim = two ? fmaxf(top_p, 0.9f) : top_p;
+        int kcap = top_k < n ? top_k : n;
         if (kcap > kSelCap) kcap = kSelCap;
         float cum = 0.f;
         int nsel = 0;
@@ -435,8 +441,8 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
         // the two draws (normal, RAS high-temperature); warp 0 / warp 1
         const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
         if (w < (two ? 2 : 1)) {
-            const float T = w == 0 ? a.temperature : 1.0f;
-            const float tp = w == 0 ? a.top_p : 0.9f;
+            const float T = w == 0 ? temperature : 1.0f;
+            const float tp = w == 0 ? top_p : 0.9f;
             const float Tc = fmaxf(T, 1e-5f);
             // survivors: rank 0 always; rank r kept iff cum[r] <= top_p (and r < top_k, implied)
             int ns = 1;
@@ -447,14 +453,17 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
             float zz = 0.f;
             for (int r = lane; r < ns; r += 32) zz += expf(rbf(sel_v[r] / Tc) - mx);
             zz = warp_sum(zz);
-            const unsigned long long off = a.rng_offset ? *a.rng_offset : 0ull;
+            // RNG stream: per call (seed, global frame counter, slot) or, with slot control, per request
+            // (its own seed and frame index, no slot) so that the draw does not depend on the schedule
+            const unsigned long long off =
+                per_slot ? static_cast<unsigned long long>(a.ctl.n_out[slot]) : (a.rng_offset ? *a.rng_offset : 0ull);
+            const uint32_t lane_id = per_slot ? 0u : static_cast<uint32_t>(slot);
             ArgMax best{-INFINITY, 0x7fffffff};
             for (int r = lane; r < ns; r += 32) {
                 const float pr = rbf(expf(rbf(sel_v[r] / Tc) - mx) / zz);
                 uint32_t rnd[4];
-                philox4x32(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32),
-                           static_cast<uint32_t>(off), static_cast<uint32_t>(off >> 32),
-                           static_cast<uint32_t>(slot),
+                philox4x32(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32),
+                           static_cast<uint32_t>(off), static_cast<uint32_t>(off >> 32), lane_id,
                            static_cast<uint32_t>((a.draw_id * 2 + w) * kSelCap + r), rnd);
                 const float u = (static_cast<float>(rnd[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
                 const float q = -logf(u);
@@ -496,6 +505,9 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
                 a.ras_window[slot * 10 + 9] = tok;
             }
             if (a.finished && tok == a.im_end_id) a.finished[slot] = 1;
+            // the reference's loop tests <|im_end|> from the second frame on (the prefill's token is not
+            // tested, inference.py:336-352 then :233)
+            if (per_slot && tok == a.im_end_id && a.ctl.n_out[slot] >= 1) a.ctl.state[slot] = 3;
         } else {
             ct[a.cb_index + 1] = s_choice[0];
         }
@@ -507,6 +519,7 @@ __global__ void frame_end_kernel(FrameEndArgs a) {
     pdl_wait();
     const int row = blockIdx.x;
     const int slot = a.row_slot ? a.row_slot[row] : row;
+    if (!slot_live(a.ctl, slot)) return;
     const int f = a.n_out[slot];
     if (threadIdx.x < a.ncols && f < a.T_cap)
         a.out_tokens[(static_cast<size_t>(slot) * a.ncols + threadIdx.x) * a.T_cap + f] =
@@ -514,9 +527,14 @@ __global__ void frame_end_kernel(FrameEndArgs a) {
     __syncthreads();
     if (threadIdx.x == 0) {
         a.n_out[slot] = f + 1;
+        bool advance = true;
+        if (a.ctl.state != nullptr && (a.ctl.state[slot] == 3 || f + 1 >= a.ctl.limit[slot])) {
+            a.ctl.state[slot] = 2;  // frozen: position and counters stay at the last frame
+            advance = false;
+        }
         if (a.set_pos_rows)
-            a.pos[slot] = a.row_pos_src[a.set_pos_rows[row]] + 1;
-        else
+            a.pos[slot] = a.row_pos_src[a.set_pos_rows[row]] + (advance ? 1 : 0);
+        else if (advance)
             a.pos[slot] = a.pos[slot] + 1;
     }
 }
@@ -605,7 +623,7 @@ int launch_swiglu(const SwigluArgs& a, cudaStream_t st) {
 int launch_sample(const SampleArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
     FSB_CHECK(a.n > 0 && a.n <= kSampleMaxN, "sample: n=%d out of range", a.n);
-    FSB_CHECK(a.top_k >= 1, "sample: top_k must be >= 1");
+    FSB_CHECK(a.ctl.state != nullptr || a.top_k >= 1, "sample: top_k must be >= 1");
     FSB_LAUNCH(sample_kernel, dim3(a.rows), dim3(kSampleThreads), 0, st, a);
     return 0;
 }

@@ -162,8 +162,29 @@ struct SwigluArgs {
 };
 int launch_swiglu(const SwigluArgs& a, cudaStream_t st);
 
+// Per-slot request control (continuous batching). When `state` is non-null the frame kernels
+// take the sampling parameters, the RNG stream and the stop rule from these arrays instead of the per-call
+// values, so that every request computes exactly what it would compute alone, whatever shares the batch.
+//   state: 0 idle, 1 active, 2 finished (frozen until the host retires it), 3 finishing (set by the slow
+//   sampler on <|im_end|>; this frame is still recorded, inference.py:233-234)
+struct SlotCtl {
+    int* state;
+    const int* limit;  // frames this request may produce (the prefill frame included)
+    const float* temperature;
+    const float* top_p;
+    const int* top_k;
+    const unsigned long long* seed;
+    const int* n_out;  // frames produced so far = RNG counter of the request
+};
+__device__ __forceinline__ bool slot_live(const SlotCtl& c, int slot) {
+    if (c.state == nullptr) return true;
+    const int s = c.state[slot];
+    return s == 1 || s == 3;
+}
+
 struct SampleArgs {
     DepFlag wait;
+    SlotCtl ctl;
     Partials parts;  // logits of the (restricted) head: n entries per row
     int n;           // number of candidate entries (<= 8192)
     int rows;
@@ -193,6 +214,7 @@ int launch_sample(const SampleArgs& a, cudaStream_t st);
 //   out_tokens[slot][c][n_out[slot]] = cur_tok[slot][c]; n_out[slot]++;
 //   pos[slot] = set_pos_rows ? row_pos_src[set_pos_rows[row]] + 1 : pos[slot] + 1;   step++
 struct FrameEndArgs {
+    SlotCtl ctl;
     const int* cur_tok;
     int* out_tokens;  // [slots][C+1][T_cap]
     int* n_out;

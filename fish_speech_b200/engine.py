@@ -128,6 +128,7 @@ class LmEngine:
         self.debug = debug
         self._views = {}
         self._ctx_bound = 0  # upper bound of every slot's length, tracked on the host
+        self.slot_control = False
 
     def close(self):
         if getattr(self, "h", None):
@@ -156,6 +157,12 @@ class LmEngine:
             "finished": ((self.max_batch,), "<i4"),
             "cur_tok": ((self.max_batch, C1), "<i4"),
             "ras_window": ((self.max_batch, 10), "<i4"),
+            "slot_state": ((self.max_batch,), "<i4"),
+            "slot_limit": ((self.max_batch,), "<i4"),
+            "slot_temperature": ((self.max_batch,), "<f4"),
+            "slot_top_p": ((self.max_batch,), "<f4"),
+            "slot_top_k": ((self.max_batch,), "<i4"),
+            "slot_seed": ((self.max_batch,), "<i8"),
             "pk_trace": ((1024,), "<i8"),
             "slow_logits": ((self.max_batch, self.head_rows), "<f4"),
             "fast_logits": ((c.num_codebooks, self.max_batch, c.codebook_size), "<f4"),
@@ -188,12 +195,22 @@ class LmEngine:
         """For callers that place tokens at explicit positions (decode_one_token_ar / decode_n_tokens)."""
         self._grow_bound(n)
 
+    def set_context_bound_exact(self, n: int):
+        """For a scheduler that knows every live slot's length: the bound may also shrink."""
+        self._ctx_bound = 0
+        self._grow_bound(max(1, n))
+
+    def set_slot_control(self, enable: bool):
+        """Per-slot sampling parameters / stop rule / RNG stream (include/fishb200.h fsb_lm_set_slot_control)."""
+        _lib.check(self.lib.fsb_lm_set_slot_control(self.h, int(bool(enable))))
+        self.slot_control = bool(enable)
+
     def reset(self):
         self._ctx_bound = 0
         with torch.cuda.device(self.device):
             _lib.check(self.lib.fsb_lm_reset(self.h, _stream()))
 
-    def prefill(self, prompts: Sequence[torch.Tensor], slots: Sequence[int], sp: _lib.Sampling,
+    def prefill(self, prompts: Sequence[torch.Tensor], slots: Sequence[int], sp: Optional[_lib.Sampling],
                 start_pos: Optional[Sequence[int]] = None, do_sample: bool = True) -> None:
         """prompts[k]: integer tensor [C+1, T_k] (row 0 token ids, rows 1..C codes) for slot slots[k]."""
         C1 = self.cfg.num_codebooks + 1
@@ -244,15 +261,17 @@ class LmEngine:
                 d_gsl = torch.tensor(gsl, dtype=torch.int32, device=dev)
                 _lib.check(self.lib.fsb_lm_prefill(
                     self.h, d_tok.data_ptr(), d_slot.data_ptr(), d_pos.data_ptr(), rows, d_last.data_ptr(),
-                    d_gsl.data_ptr(), len(grp), int(do_sample and final), C.byref(sp), _stream()))
+                    d_gsl.data_ptr(), len(grp), int(do_sample and final), C.byref(sp) if sp is not None else None,
+                    _stream()))
                 # index tensors must outlive the asynchronous kernels that read them
                 self._inflight = (d_tok, d_slot, d_pos, d_last, d_gsl)
 
-    def decode(self, batch: int, nframes: int, sp: _lib.Sampling, use_graph: bool = True) -> None:
+    def decode(self, batch: int, nframes: int, sp: Optional[_lib.Sampling], use_graph: bool = True) -> None:
         import os
 
         if os.environ.get("FSB_NO_GRAPH") == "1":  # diagnostic: eager launches instead of graph replays
             use_graph = False
         self._grow_bound(self._ctx_bound + nframes)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.fsb_lm_decode(self.h, batch, nframes, C.byref(sp), int(use_graph), _stream()))
+            _lib.check(self.lib.fsb_lm_decode(self.h, batch, nframes, C.byref(sp) if sp is not None else None,
+                                               int(use_graph), _stream()))

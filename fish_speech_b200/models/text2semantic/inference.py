@@ -11,6 +11,7 @@ The CPU-side prompt builder (Conversation / ContentSequence / tokenizer) is the 
 """
 from __future__ import annotations
 
+import os
 import queue
 import threading
 import time
@@ -308,11 +309,11 @@ def group_turns_into_batches(turns: list[str], max_speakers: int = 3, max_bytes:
     return batches
 
 
-def generate_long(
+def _generate_long_plan(
     *,
     model,
     device: Union[str, torch.device],
-    decode_one_token: Callable,
+    decode_one_token: Optional[Callable] = None,
     text: str,
     num_samples: int = 1,
     max_new_tokens: int = 0,
@@ -326,7 +327,10 @@ def generate_long(
     prompt_text: Optional[Union[str, list[str]]] = None,
     prompt_tokens: Optional[Union[torch.Tensor, list[torch.Tensor]]] = None,
 ):
-    """inference.py:523-733: build the conversation, generate chunk by chunk, yield codes per chunk."""
+    """inference.py:523-733 as a coroutine: build the conversation and walk the chunk loop, but hand every
+    `generate` call to the driver. Yields ("generate", kwargs) and expects the [C+1, T+n] result to be sent
+    back; yields ("response", GenerateResponse) for everything the reference's generator yields. One
+    request at a time (generate_long) and the slot scheduler (launch_thread_safe_queue) drive the same plan."""
     assert 0 < top_p <= 1, "top_p must be in (0, 1]"
     assert 0 < temperature < 2, "temperature must be in (0, 2)"
     TextPart, VQPart, Conversation, Message = _reference_frontend()
@@ -386,11 +390,8 @@ def generate_long(
             encoded = encoded.to(device=device)
             prompt_length = encoded.size(1)
             t0 = time.perf_counter()
-            y = generate(model=model, prompt=encoded, max_new_tokens=max_new_tokens, audio_masks=audio_masks,
-                         audio_parts=audio_parts, decode_one_token=decode_one_token, temperature=temperature,
-                         top_p=top_p, top_k=top_k)
-            if torch.cuda.is_available():
-                torch.cuda.synchronize()
+            y = yield ("generate", dict(prompt=encoded, max_new_tokens=max_new_tokens, audio_masks=audio_masks,
+                                        audio_parts=audio_parts, temperature=temperature, top_p=top_p, top_k=top_k))
             t_batch = time.perf_counter() - t0
             tokens_generated = y.size(1) - prompt_length
             tokens_sec = tokens_generated / t_batch if t_batch > 0 else 0
@@ -400,11 +401,41 @@ def generate_long(
             assert (codes >= 0).all(), f"Negative code found: {codes}"
             conversation.append(Message(role="assistant", parts=[VQPart(codes=codes.cpu(), cal_loss=False)],
                                         cal_loss=False, modality="voice", add_im_start=True, add_im_end=True))
-            yield GenerateResponse(action="sample", codes=codes, text=batch_text)
+            yield ("response", GenerateResponse(action="sample", codes=codes, text=batch_text))
             del y, encoded
         if torch.cuda.is_available():
             logger.info(f"GPU Memory used: {torch.cuda.max_memory_reserved() / 1e9:.02f} GB")
-        yield GenerateResponse(action="next")
+        yield ("response", GenerateResponse(action="next"))
+
+
+def generate_long(*, model, decode_one_token: Callable = None, **kwargs):
+    """inference.py:523-733: yields GenerateResponse("sample", codes [C, n], text) per chunk, then ("next")."""
+    plan = _generate_long_plan(model=model, **kwargs)
+    reply = None
+    while True:
+        try:
+            kind, payload = plan.send(reply)
+        except StopIteration:
+            return
+        reply = None
+        if kind == "generate":
+            reply = generate(model=model, decode_one_token=decode_one_token or decode_one_token_ar,
+                             seed=_next_seed(model), **payload)
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+        else:
+            yield payload
+
+
+def _next_seed(model) -> int:
+    """Philox key of the next `generate` call: torch's seed (what the CLI's --seed sets) advanced by a per-model
+    call counter, so that consecutive chunks / requests do not replay one random stream. Re-seeding torch
+    restarts the sequence."""
+    base = int(torch.initial_seed())
+    last, n = getattr(model, "_seed_state", (None, 0))
+    n = n + 1 if last == base else 0
+    model._seed_state = (base, n)
+    return (base + 0x9E3779B97F4A7C15 * n) & 0x7FFFFFFFFFFFFFFF
 
 
 @dataclass
@@ -419,14 +450,90 @@ class GenerateRequest:
     response_queue: queue.Queue
 
 
+def serve_requests(model, input_queue: "queue.Queue", max_slots: int, frames_per_poll: int = 8,
+                   batcher=None) -> None:
+    """Worker loop of the slot scheduler: every queued request's `generate_long` plan advances concurrently,
+    their `generate` calls share the decode frames (fish_speech_b200/scheduler.py). Responses of one request
+    arrive in the reference's order on its own response queue; `None` shuts the loop down once the running
+    requests are finished."""
+    from ...scheduler import ContinuousBatcher, SlotRequest
+
+    if batcher is None:
+        batcher = ContinuousBatcher(model, max_slots=max_slots, frames_per_poll=frames_per_poll)
+    live = 0  # plans not yet exhausted
+    closing = False
+
+    def advance(plan, response_queue, reply):
+        """Run a plan until it asks for the next `generate` (submitted to the batcher) or ends."""
+        nonlocal live
+        try:
+            while True:
+                kind, payload = plan.send(reply)
+                reply = None
+                if kind == "response":
+                    response_queue.put(WrappedGenerateResponse(status="success", response=payload))
+                    continue
+                if payload.get("audio_parts") is not None:
+                    raise NotImplementedError("audio_parts is not supported (nor by the reference model)")
+                batcher.submit(SlotRequest(
+                    prompt=payload["prompt"], max_new_tokens=payload["max_new_tokens"],
+                    temperature=payload["temperature"], top_p=payload["top_p"], top_k=payload["top_k"],
+                    seed=_next_seed(model),
+                    on_done=lambda r, plan=plan, q=response_queue: advance(plan, q, r.result)))
+                return
+        except StopIteration:
+            live -= 1
+        except Exception as e:
+            logger.error(traceback.format_exc())
+            response_queue.put(WrappedGenerateResponse(status="error", response=e))
+            live -= 1
+
+    try:
+        while True:
+            # take everything that is waiting; block only when there is nothing to compute
+            while not closing:
+                try:
+                    item = input_queue.get(block=(live == 0 and batcher.idle()))
+                except queue.Empty:
+                    break
+                if item is None:
+                    closing = True
+                    break
+                live += 1
+                try:
+                    plan = _generate_long_plan(model=model, **{k: v for k, v in item.request.items()
+                                                               if k != "decode_one_token"})
+                except Exception as e:  # pragma: no cover - argument errors surface on first send
+                    item.response_queue.put(WrappedGenerateResponse(status="error", response=e))
+                    live -= 1
+                    continue
+                advance(plan, item.response_queue, None)
+            if live == 0 and closing:
+                return
+            batcher.step()
+    finally:
+        batcher.close()
+
+
 def launch_thread_safe_queue(checkpoint_path, device, precision, compile: bool = False):
     """inference.py:736-799: the model lives in ONE daemon worker thread fed by a queue; `None` shuts
-    it down; errors are returned as WrappedGenerateResponse(status="error", response=exc)."""
+    it down; errors are returned as WrappedGenerateResponse(status="error", response=exc).
+
+    FSB_SERVE_SLOTS=n (2..32) makes the worker a slot scheduler that runs up to n requests concurrently
+    (`serve_requests`), each with a KV cache of FSB_SERVE_KV_LEN positions (default 8192; a slot costs
+    147 456 B per position at the S2-Pro geometry). Unset / 1: the reference's one-at-a-time loop."""
     input_queue = queue.Queue()
     init_event = threading.Event()
+    slots = max(1, min(32, int(os.environ.get("FSB_SERVE_SLOTS", "1"))))
 
     def worker():
         model, decode_one_token = init_model(checkpoint_path, device, precision, compile=compile)
+        if slots > 1:
+            kv = min(int(os.environ.get("FSB_SERVE_KV_LEN", "8192")), model.config.max_seq_len)
+            model.setup_caches(max_batch_size=slots, max_seq_len=kv, dtype=model.dtype)
+            init_event.set()
+            serve_requests(model, input_queue, slots)
+            return
         model.setup_caches(max_batch_size=1, max_seq_len=model.config.max_seq_len, dtype=model.dtype)
         init_event.set()
         while True:

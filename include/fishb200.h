@@ -123,12 +123,27 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* s, int 
  * far). Sizes the attention score buffer; must be set before prefill / decode whenever it grows. */
 int fsb_lm_set_context_bound(fsb_lm* h, int max_positions);
 
-/* Reset per-slot generation state (frame counters, RAS window, finished flags). */
+/* Per-slot request control — continuous batching over the KV slots, i.e. the batched form of the loop
+ * in decode_n_tokens / generate (inference.py:184-359) that the reference runs for one request at a
+ * time behind launch_thread_safe_queue (inference.py:748-799). When enabled, prefill and decode ignore
+ * `s` (may be NULL) and read, per slot, the device arrays
+ *   "slot_state" int32 (0 idle, 1 active, 2 finished, 3 finishing), "slot_limit" int32 (frames allowed,
+ *   the prefill's frame included), "slot_temperature" f32, "slot_top_p" f32 (both already rounded to
+ *   bf16 by the host, as the reference's tensors are), "slot_top_k" int32, "slot_seed" uint64.
+ * The host writes them (fsb_lm_buffer) before prefilling a request into a slot; the frame kernels stop
+ * a slot on <|im_end|> (from its second frame on) or at its limit, freeze its position and counters,
+ * and set state = 2; the host collects "out_tokens"[slot][:, :n_out[slot]] and sets the state to 0.
+ * The random stream of a request depends on (seed, own frame index, draw) only: a request produces
+ * the same tokens alone or with any neighbours, in any slot. */
+int fsb_lm_set_slot_control(fsb_lm* h, int enable);
+
+/* Reset per-slot generation state (frame counters, RAS window, finished flags, slot states). */
 int fsb_lm_reset(fsb_lm* h, void* stream);
 
 /* Named device buffers of the handle, for reading results and for tests:
  *   "out_tokens" int32 [max_batch][C+1][max_frames], "n_out" int32 [max_batch], "pos" int32 [max_batch],
  *   "finished" int32 [max_batch], "cur_tok" int32 [max_batch][C+1], "ras_window" int32 [max_batch][10],
+ *   the slot-control arrays listed at fsb_lm_set_slot_control,
  *   debug only: "slow_logits" f32 [max_batch][head_rows], "fast_logits" f32 [C][max_batch][codebook_size],
  *   "hidden" bf16 [32][dim], "dbg_x" bf16 [n_layer+1][32][dim] */
 int fsb_lm_buffer(fsb_lm* h, const char* name, void** d_ptr, size_t* bytes);

@@ -97,3 +97,93 @@ def test_generate_long_validates_sampling_args():
         next(inf.generate_long(model=None, device="cpu", decode_one_token=None, text="x", top_p=0.0))
     with pytest.raises(AssertionError):
         next(inf.generate_long(model=None, device="cpu", decode_one_token=None, text="x", temperature=2.5))
+
+
+class _FakeBatcher:
+    """Stands in for scheduler.ContinuousBatcher: a request finishes after ceil(limit / 4) steps and its
+    result is the prompt followed by `max_new_tokens` copies of its seed's low byte."""
+
+    def __init__(self, slots):
+        self.slots, self.waiting, self.active, self.max_active, self.closed = slots, [], [], 0, False
+
+    def submit(self, r):
+        self.waiting.append(r)
+
+    def idle(self):
+        return not self.waiting and not self.active
+
+    def step(self):
+        while self.waiting and len(self.active) < self.slots:
+            r = self.waiting.pop(0)
+            self.active.append([r, (r.max_new_tokens + 3) // 4])
+        self.max_active = max(self.max_active, len(self.active))
+        for e in list(self.active):
+            e[1] -= 1
+            if e[1] <= 0:
+                self.active.remove(e)
+                r = e[0]
+                r.result = torch.cat([r.prompt, torch.full((r.prompt.size(0), r.max_new_tokens), 7)], dim=1)
+                r.on_done(r)
+
+    def close(self):
+        self.closed = True
+
+
+def _fake_plan(*, model, text, chunks=2, fail=False, **kw):
+    """Shape of _generate_long_plan: per chunk one generate request, then a sample response; 'next' at the end."""
+    for c in range(chunks):
+        y = yield ("generate", dict(prompt=torch.full((3, 2 + c), len(text)), max_new_tokens=4 * (c + 1) + len(text),
+                                    audio_masks=None, audio_parts=None, temperature=0.7, top_p=0.7, top_k=30))
+        if fail:
+            raise RuntimeError("boom")
+        yield ("response", inf.GenerateResponse(action="sample", codes=y[1:, 2 + c:], text=f"{text}#{c}"))
+    yield ("response", inf.GenerateResponse(action="next"))
+
+
+def test_slot_scheduler_worker_interleaves_requests(monkeypatch):
+    """serve_requests: several queued requests advance together, each response queue sees the reference's
+    sequence (sample per chunk, then next), an exception reaches only its own request, None shuts down."""
+    import queue as Q
+
+    monkeypatch.setattr(inf, "_generate_long_plan", _fake_plan)
+    fb = _FakeBatcher(slots=3)
+    q = Q.Queue()
+    outs = []
+    for i, (text, fail) in enumerate([("a", False), ("bbbbbb", False), ("cc", True), ("ddd", False)]):
+        rq = Q.Queue()
+        outs.append(rq)
+        q.put(inf.GenerateRequest(request=dict(text=text, fail=fail, chunks=2), response_queue=rq))
+    q.put(None)
+    inf.serve_requests(_FakeModel(), q, 3, batcher=fb)
+    assert fb.closed and fb.max_active == 3  # three requests really shared the scheduler steps
+
+    def drain(rq):
+        items = []
+        while not rq.empty():
+            items.append(rq.get_nowait())
+        return items
+
+    for i, text in [(0, "a"), (1, "bbbbbb"), (3, "ddd")]:
+        items = drain(outs[i])
+        assert [it.status for it in items] == ["success"] * 3
+        assert [it.response.action for it in items] == ["sample", "sample", "next"]
+        assert [it.response.text for it in items[:2]] == [f"{text}#0", f"{text}#1"]
+        assert items[0].response.codes.shape == (2, 4 + len(text))
+        assert items[1].response.codes.shape == (2, 8 + len(text))
+    bad = drain(outs[2])
+    assert len(bad) == 1 and bad[0].status == "error" and isinstance(bad[0].response, RuntimeError)
+
+
+def test_generate_long_drives_the_same_plan(monkeypatch):
+    """generate_long = the plan driven one `generate` at a time (inference.py:611-721)."""
+    monkeypatch.setattr(inf, "_generate_long_plan", _fake_plan)
+    calls = []
+
+    def fake_generate(*, model, prompt, max_new_tokens, seed, **kw):
+        calls.append(seed)
+        return torch.cat([prompt, torch.zeros(prompt.size(0), max_new_tokens, dtype=prompt.dtype)], dim=1)
+
+    monkeypatch.setattr(inf, "generate", fake_generate)
+    out = list(inf.generate_long(model=_FakeModel(), decode_one_token=None, text="xy", chunks=3))
+    assert [r.action for r in out] == ["sample"] * 3 + ["next"]
+    assert len(set(calls)) == 3  # every generate call gets its own Philox key
