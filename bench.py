@@ -259,7 +259,7 @@ def voice_clone_bench(args):
 
 def serve_bench(args):
     """a queue of requests with RAGGED lengths (the fixed-length headline hides what the
-    reference's one-request-at-a-time worker and a static batch both lose). 96 requests, 64-token prompts,
+    reference's one-request-at-a-time worker and a static batch both lose). 192 requests, 64-token prompts,
     64..256 frames each (seeded), greedy, LM stage only (the codec stage is the same work either way).
     Measured twice on the same requests: static batches of 32 in arrival order (`generate_batch`: a batch
     lasts as long as its longest request) and the slot scheduler (`ContinuousBatcher`, 32 slots)."""
@@ -271,7 +271,7 @@ def serve_bench(args):
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    NREQ, SLOTS = 96, 32
+    NREQ, SLOTS = 192, 32
     cfg = s2pro_args(max_seq_len=T_PROMPT + 256)
     w = synthetic.lm_state_dict(cfg, dev)
     w["embeddings.weight"][S2PRO_IM_END_ID] = 0  # lengths are set by the per-request budgets

@@ -40,7 +40,11 @@ class SlotRequest:
 
 
 class ContinuousBatcher:
-    def __init__(self, model, max_slots: int = 32, frames_per_poll: int = 8):
+    def __init__(self, model, max_slots: int = 32, frames_per_poll: int = 8, min_free_to_admit: int = 1):
+        """`frames_per_poll`: decode frames between two looks at the device-side slot states (a finished slot
+        idles for at most that many frames). `min_free_to_admit`: admissions wait until that many slots are
+        free (or nothing is running) — every admission is one extra prefill pass + first frame that streams
+        all weights for the new rows only, so grouping them trades admission latency for throughput."""
         from .models.text2semantic.inference import _ensure_engine
 
         if not 1 <= max_slots <= 32:
@@ -50,6 +54,7 @@ class ContinuousBatcher:
         self.eng = _ensure_engine(model, max_slots)
         self.max_slots = max_slots
         self.frames_per_poll = int(frames_per_poll)
+        self.min_free_to_admit = max(1, int(min_free_to_admit))
         self.waiting: list[SlotRequest] = []
         self.active: dict[int, SlotRequest] = {}
         self._len: dict[int, int] = {}  # slot -> upper bound of its context length
@@ -94,6 +99,8 @@ class ContinuousBatcher:
     def _admit(self):
         free = [s for s in range(self.max_slots) if s not in self.active]
         if not free or not self.waiting:
+            return
+        if self.active and len(free) < min(self.min_free_to_admit, len(self.waiting)):
             return
         batch, slots = [], []
         budget = self.eng.max_rows  # one prefill pass worth of rows per step keeps decode latency bounded
