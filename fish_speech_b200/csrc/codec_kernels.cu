@@ -267,7 +267,9 @@ int fsb_conv_gemm(const void* d_x, int B, int T_in, int C_in, int row_stride, lo
     FSB_CHECK(taps >= 1 && taps <= kMaxTaps, "conv_gemm: taps=%d out of range", taps);
     FSB_CHECK(kpad % 64 == 0, "conv_gemm: kpad must be a multiple of 64");
     FSB_CHECK(d_out0 || d_out1, "conv_gemm: no output");
-    const int bn = C_out <= 32 ? 32 : (C_out <= 64 ? 64 : (C_out <= 128 ? 128 : 256));
+    // tile width along the output channels: no padding waste for the 192- and 384-channel blocks (UMMA N = 192)
+    const int bn = C_out <= 32 ? 32 : (C_out <= 64 ? 64 : (C_out <= 128 ? 128 : ((C_out % 256 != 0 && C_out % 192 == 0) ? 192 : 256)));
+    const int two = bn <= 128 ? 2 : 1;  // CTAs per SM (shared memory: 3 x 32 KB stages each; TMEM: 2 x 256 columns)
     ConvKey key;
     memset(&key, 0, sizeof(key));
     key.x = d_x; key.w = d_w; key.B = B; key.T_in = T_in; key.T_out = T_out; key.C_in = C_in;
@@ -294,8 +296,8 @@ int fsb_conv_gemm(const void* d_x, int B, int T_in, int C_in, int row_stride, lo
             np.p.a_hint = kEvictNormal;
             np.p.b_hint = kEvictLast;  // the weights are re-read by every time tile
             FSB_TRY(gemm_init());
-            FSB_TRY(gemm_plan_init(&np, A, Bw, bn, 4, cdiv(T_out, 128), cdiv(C_out, bn), B));
-            FSB_TRY(gemm_plan_tiled(&np, cdiv(T_out, 128), cdiv(C_out, bn), B));
+            FSB_TRY(gemm_plan_init(&np, A, Bw, bn, bn == 128 ? 3 : 4, cdiv(T_out, 128), cdiv(C_out, bn), B));
+            FSB_TRY(gemm_plan_tiled(&np, cdiv(T_out, 128), cdiv(C_out, bn), B, two));
             it = g_conv_plans.emplace(key, np).first;
         }
         plan = it->second;

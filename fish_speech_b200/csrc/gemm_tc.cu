@@ -31,12 +31,28 @@ __device__ __forceinline__ float snake_fast(float v, float a, float ia) {
     return fmaf(ia * s, s, v);
 }
 
+__device__ __forceinline__ bool epilogue_fast(const GemmParams& p, int jbase) {
+    return !p.chan_on_i && (p.o_js == 1) && !p.out_f32 && ((p.o_is & 7) == 0) && ((p.o_zs & 7) == 0) &&
+           (jbase + 32 <= p.rows_j);
+}
+
+// The residual of a chunk (4 x 16 bytes per thread) is requested BEFORE the accumulator is read from TMEM and
+// before any store of the chunk: the stores may alias the residual buffer (in-place residual stream), so the
+// compiler cannot hoist these loads itself, and one 16-byte load in flight per thread left the 1x1 convs of
+// the wide-time blocks latency-bound at ~2 TB/s.
+__device__ __forceinline__ void epilogue_preload(const GemmParams& p, int i, int jbase, int z, uint4 (&rr)[4]) {
+    if (p.resid == nullptr || !epilogue_fast(p, jbase)) return;
+    const size_t rowoff = static_cast<size_t>(z) * p.o_zs + static_cast<size_t>(i) * p.o_is;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rr[q] = *reinterpret_cast<const uint4*>(p.resid + rowoff + jbase + q * 8);
+}
+
 template <int BN>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* r, int i, int jbase, int z) {
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* r, const uint4 (&rr)[4], int i,
+                                               int jbase, int z) {
     const size_t zoff = static_cast<size_t>(z) * p.o_zs;
     const size_t rowoff = zoff + static_cast<size_t>(i) * p.o_is;
-    const bool fast = !p.chan_on_i && (p.o_js == 1) && !p.out_f32 && ((p.o_is & 7) == 0) && ((p.o_zs & 7) == 0) &&
-                      (jbase + 32 <= p.rows_j);
+    const bool fast = epilogue_fast(p, jbase);
     if (fast) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -61,7 +77,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
                 v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
             }
             if (p.resid) {
-                const uint4 u = *reinterpret_cast<const uint4*>(p.resid + rowoff + j);
+                const uint4 u = rr[q];
                 v[0] += bf_lo(u.x); v[1] += bf_hi(u.x); v[2] += bf_lo(u.y); v[3] += bf_hi(u.y);
                 v[4] += bf_lo(u.z); v[5] += bf_hi(u.z); v[6] += bf_lo(u.w); v[7] += bf_hi(u.w);
             }
@@ -126,13 +142,14 @@ struct GemmRoles {
 };
 
 template <int BN, int MODE>
-__global__ void __launch_bounds__(GemmRoles<MODE>::kThreads, MODE == 0 ? 2 : 1)
+__global__ void __launch_bounds__(GemmRoles<MODE>::kThreads, (MODE == 0 || BN <= 128) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int kBTileBytes = BN * kBlockK * 2;
     constexpr int kStageBytes = kATileBytes + kBTileBytes;
-    constexpr int kTmemCols = 2 * BN;  // two accumulators: epilogue of item n overlaps MMA of n+1
+    // two accumulators: epilogue of item n overlaps MMA of n+1 (allocation size must be a power of two)
+    constexpr int kTmemCols = BN == 192 ? 512 : 2 * BN;
     constexpr int kEpiWarps = GemmRoles<MODE>::kEpiWarps;
     constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 
@@ -351,9 +368,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
                 for (int c0 = half * 32; c0 < BN; c0 += 32 * (kEpiWarps / 4)) {
                     uint32_t r[32];
+                    uint4 rr[4];
+                    const bool live = i_ok && j0 + c0 < p.rows_j;
+                    if (live) epilogue_preload(p, i, j0 + c0, z, rr);
                     tmem_ld32(taddr + c0, r);
                     tmem_ld_wait();
-                    if (i_ok && j0 + c0 < p.rows_j) epilogue_chunk<BN>(p, r, i, j0 + c0, z);
+                    if (live) epilogue_chunk<BN>(p, r, rr, i, j0 + c0, z);
                 }
             }
             // release the accumulator to the MMA warp
@@ -445,7 +465,7 @@ int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
 
 int gemm_plan_init(GemmPlan* plan, const GemmOperand& A, const GemmOperand& B, int bn, int stages,
                    int tiles_i, int tiles_j, int batch) {
-    FSB_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 256, "unsupported BN %d", bn);
+    FSB_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 192 || bn == 256, "unsupported BN %d", bn);
     FSB_TRY(make_tmap(&plan->tmA, A, kBlockM));
     FSB_TRY(make_tmap(&plan->tmB, B, bn));
     const int stage_bytes = kATileBytes + bn * kBlockK * 2;
@@ -513,13 +533,16 @@ int gemm_plan_streamk(GemmPlan* plan, int tiles_i, int kblocks, int num_ctas, bo
     return 0;
 }
 
-int gemm_plan_tiled(GemmPlan* plan, int tiles_i, int tiles_j, int batch) {
+int gemm_plan_tiled(GemmPlan* plan, int tiles_i, int tiles_j, int batch, int ctas_per_sm) {
     const long long total = static_cast<long long>(tiles_i) * tiles_j * batch;
     FSB_CHECK(total > 0 && total < (1ll << 31), "gemm_plan_tiled: bad tile count");
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long ctas = total < sms ? total : sms;  // one persistent CTA per SM (smem-limited)
+    // persistent CTAs: one per SM, or two where shared memory and TMEM allow (narrow tiles: more epilogue
+    // warps in flight for the memory-bound layers)
+    const long long slots = static_cast<long long>(sms) * (ctas_per_sm > 1 ? 2 : 1);
+    const long long ctas = total < slots ? total : slots;
     plan->p.tiled_total = static_cast<int>(total);
     plan->p.tiled_ti = tiles_i;
     plan->p.tiled_tj = tiles_j;
@@ -544,6 +567,7 @@ int gemm_init() {
                                   227 * 1024));
     FSB_GEMM_ATTR(32, 0) FSB_GEMM_ATTR(64, 0) FSB_GEMM_ATTR(128, 0) FSB_GEMM_ATTR(256, 0)
     FSB_GEMM_ATTR(32, 1) FSB_GEMM_ATTR(64, 1) FSB_GEMM_ATTR(128, 1) FSB_GEMM_ATTR(256, 1)
+    FSB_GEMM_ATTR(192, 0) FSB_GEMM_ATTR(192, 1)
 #undef FSB_GEMM_ATTR
     return 0;
 }
@@ -553,6 +577,7 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
         case 32: return launch_bn<32>(plan, stream);
         case 64: return launch_bn<64>(plan, stream);
         case 128: return launch_bn<128>(plan, stream);
+        case 192: return launch_bn<192>(plan, stream);
         case 256: return launch_bn<256>(plan, stream);
     }
     set_error("gemm_launch: bad BN %d", plan.bn);

@@ -88,7 +88,7 @@ int gemm_plan_init(GemmPlan* plan, const GemmOperand& A, const GemmOperand& B, i
 // [0, nparts[t]) of the workspace.
 int gemm_plan_streamk(GemmPlan* plan, int tiles_i, int kblocks, int num_ctas, bool keep_empty_ctas = false);
 // Persistent tiled schedule (no table): tiles_i x tiles_j x batch full-K tiles spread over <= 2 CTAs per SM.
-int gemm_plan_tiled(GemmPlan* plan, int tiles_i, int tiles_j, int batch);
+int gemm_plan_tiled(GemmPlan* plan, int tiles_i, int tiles_j, int batch, int ctas_per_sm = 1);
 void gemm_plan_free(GemmPlan* plan);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 int gemm_init();  // set kernel attributes (idempotent)
