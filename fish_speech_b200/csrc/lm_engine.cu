@@ -60,6 +60,7 @@ struct fsb_lm {
     int flag_next = 0;
     static constexpr int kFlagCap = 4096;
     // per-slot request control (continuous batching): see SlotCtl in lm_kernels.cuh
+    bool fused_fast_only = false;
     bool slot_control = false;
     int* slot_state = nullptr;
     int* slot_limit = nullptr;
@@ -256,7 +257,7 @@ int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool
         LayerPlans& P = c.decode ? s.dec[l] : s.pf[l];
         if (fl) FSB_TRY(launch_dec_gemm(h, P.qkv, ready, &gd, st));
         else FSB_TRY(launch_rows(P.qkv, c.rows, st));
-        if (c.decode && h->fused_prep_attn) {
+        if (c.decode && h->fused_prep_attn && (!h->fused_fast_only || s.bf16_math)) {
             // decode rows: q/k/v post-processing, KV append and attention in one launch
             PkArgs A{};
             A.rows = c.rows; A.D = s.D; A.H = s.H; A.Hkv = s.Hkv; A.Dh = s.Dh; A.I = s.I; A.S = s.S;
@@ -677,7 +678,8 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     }
     {
         const char* ef = getenv("FSB_FUSED_ATTN");
-        h->fused_prep_attn = ef && ef[0] == '1';  // measured slower than qkv_prep + attn (6.45 vs 6.22 ms/frame): off
+        h->fused_prep_attn = ef && (ef[0] == '1' || ef[0] == '2');  // measured slower than qkv_prep + attn (6.45 vs 6.22 ms/frame): off
+        h->fused_fast_only = ef && ef[0] == '2';  // 2: only the fast stack (10-position KV)
         TRYC(pk_init());
     }
     if (h->persistent) {
