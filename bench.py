@@ -532,7 +532,7 @@ def main():
     if world > 1:
         dist.barrier()
     if rank == 0:
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported at N=1 only (rank 0's host cores)
             try:
                 v, sec, cores, sample = cpu_reference_port(1, 0, frames_per_step=3)
                 out["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample}
