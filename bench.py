@@ -385,6 +385,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     cfg = s2pro_cfg()
     B, NF = args.batch, args.frames
