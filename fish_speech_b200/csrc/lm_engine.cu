@@ -343,7 +343,7 @@ int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool
         sa.wait = gd;
         sa.done_ctr = fl ? flag_new(h) : nullptr;
         FSB_TRY(launch_swiglu(sa, st));
-        ready = DepFlag{sa.done_ctr, static_cast<unsigned>(cdiv(s.I, 256) * c.rows)};
+        ready = DepFlag{sa.done_ctr, static_cast<unsigned>(swiglu_ctas(c.rows, s.I))};
         if (fl) FSB_TRY(launch_dec_gemm(h, P.w2, ready, &gd, st));
         else FSB_TRY(launch_rows(P.w2, c.rows, st));
         ResidNormArgs r2{};

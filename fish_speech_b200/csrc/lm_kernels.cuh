@@ -173,6 +173,7 @@ struct SwigluArgs : SwigluCore {
     unsigned* done_ctr;
 };
 int launch_swiglu(const SwigluArgs& a, cudaStream_t st);
+int swiglu_ctas(int rows, int I);  // CTAs of one launch (what a dependency flag must count)
 
 // Per-slot request control (continuous batching). When `state` is non-null the frame kernels
 // take the sampling parameters, the RNG stream and the stop rule from these arrays instead of the per-call
