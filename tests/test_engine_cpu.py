@@ -187,3 +187,100 @@ def test_generate_long_drives_the_same_plan(monkeypatch):
     out = list(inf.generate_long(model=_FakeModel(), decode_one_token=None, text="xy", chunks=3))
     assert [r.action for r in out] == ["sample"] * 3 + ["next"]
     assert len(set(calls)) == 3  # every generate call gets its own Philox key
+
+
+class _FakeEngine:
+    """Host-visible behaviour of LmEngine under slot control, on CPU tensors: prefill writes the first frame of
+    every admitted slot, a decode frame appends one token per live slot and freezes a slot at its limit."""
+
+    def __init__(self, slots, kv_len=64, max_frames=32, max_rows=16):
+        self.max_batch, self.kv_len, self.max_frames, self.max_rows = slots, kv_len, max_frames, max_rows
+        self.device = torch.device("cpu")
+        z = lambda *s, dt=torch.int32: torch.zeros(*s, dtype=dt)
+        self.bufs = dict(slot_state=z(slots), slot_limit=z(slots), slot_temperature=z(slots, dt=torch.float32),
+                         slot_top_p=z(slots, dt=torch.float32), slot_top_k=z(slots), slot_seed=z(slots, dt=torch.int64),
+                         n_out=z(slots), pos=z(32), ras_window=z(slots, 10), out_tokens=z(slots, 3, max_frames))
+        self.slot_control = False
+        self.prefills, self.decodes, self.bounds = [], 0, []
+
+    def buffer(self, name):
+        return self.bufs[name]
+
+    def reset(self):
+        for k in ("slot_state", "n_out", "pos"):
+            self.bufs[k].zero_()
+
+    def set_slot_control(self, on):
+        self.slot_control = bool(on)
+
+    def set_context_bound_exact(self, n):
+        self.bounds.append(n)
+
+    def _frame(self, s):
+        b = self.bufs
+        if int(b["slot_state"][s]) != 1:
+            return
+        f = int(b["n_out"][s])
+        b["out_tokens"][s, :, f] = 100 * s + f
+        b["n_out"][s] = f + 1
+        if f + 1 >= int(b["slot_limit"][s]):
+            b["slot_state"][s] = 2
+        else:
+            b["pos"][s] += 1
+
+    def prefill(self, prompts, slots, sp, start_pos=None, do_sample=True):
+        assert sp is None and self.slot_control
+        self.prefills.append(list(slots))
+        for p, s in zip(prompts, slots):
+            self.bufs["pos"][s] = p.shape[1]
+            self._frame(s)
+
+    def decode(self, batch, nframes, sp, use_graph=True):
+        assert sp is None and batch == self.max_batch
+        self.decodes += nframes
+        for _ in range(nframes):
+            for s in range(batch):
+                self._frame(s)
+
+
+class _SchedModel:
+    def __init__(self, eng, max_seq_len=64):
+        self.engine, self.max_batch_size = eng, eng.max_batch
+        self.config = type("C", (), dict(max_seq_len=max_seq_len, num_codebooks=2))()
+
+
+def test_continuous_batcher_host_logic():
+    """scheduler.ContinuousBatcher against a fake engine: budgets (generate's max_new_tokens clamp, inference.py:
+    270-279), slot reuse, grouped admissions, retirement order, engine handed back on close."""
+    from fish_speech_b200.scheduler import ContinuousBatcher, SlotRequest
+
+    eng = _FakeEngine(slots=2)
+    model = _SchedModel(eng)
+    b = ContinuousBatcher(model, max_slots=2, frames_per_poll=4)
+    assert eng.slot_control
+    order = []
+    mk = lambda T, n, tag: SlotRequest(prompt=torch.full((3, T), tag), max_new_tokens=n, tag=tag,
+                                       on_done=lambda r: order.append(r.tag))
+    reqs = [b.submit(mk(5, 3, 0)), b.submit(mk(7, 9, 1)), b.submit(mk(4, 1, 2)), b.submit(mk(6, 0, 3))]
+    assert reqs[3]._limit == min(64 - 6, eng.max_frames)  # max_new_tokens=0 -> as many as fit
+    with pytest.raises(ValueError):
+        b.submit(mk(64, 4, 9))  # prompt as long as max_seq_len (inference.py:262-265)
+    b.run()
+    assert b.idle() and sorted(order) == [0, 1, 2, 3] and order[0] == 0  # the 3-frame request leaves first
+    assert eng.prefills[0] == [0, 1] and all(len(p) <= 2 for p in eng.prefills)  # two slots, reused afterwards
+    assert sum(len(p) for p in eng.prefills) == 4
+    for r, n in zip(reqs, [3, 9, 1, reqs[3]._limit]):
+        T = r.prompt.size(1)
+        assert r.result.shape == (3, T + n) and torch.equal(r.result[:, :T], r.prompt)
+        assert r.result[0, T:].tolist() == [100 * r.slot + f for f in range(n)]  # its own frames, in order
+    assert 0 < b.slot_frames <= b.frames_run * 2 and max(eng.bounds) <= eng.kv_len + 1
+    b.close()
+    assert not eng.slot_control and int(eng.bufs["slot_state"].sum()) == 0
+
+    # grouped admissions: with min_free_to_admit=2 a single freed slot waits for the second one
+    eng2 = _FakeEngine(slots=2)
+    b2 = ContinuousBatcher(_SchedModel(eng2), max_slots=2, frames_per_poll=2, min_free_to_admit=2)
+    for tag, n in enumerate([2, 8, 4, 4]):
+        b2.submit(mk(3, n, tag))
+    b2.run()
+    assert eng2.prefills == [[0, 1], [0, 1]]  # the short request's slot was not refilled on its own
