@@ -111,3 +111,29 @@ def test_text_batching_helpers():
     assert turns == ["<|speaker:0|>hello", "<|speaker:1|>hi there", "<|speaker:0|>bye"]
     assert group_turns_into_batches(turns, max_speakers=2, max_bytes=1000) == ["\n".join(turns[:2]), turns[2]]
     assert len(group_turns_into_batches(turns, max_speakers=5, max_bytes=20)) == 3
+
+
+@pytest.mark.parametrize("tag", ["first", "mid"])
+def test_oracle_stop_semantics_match_reference_golden(tag):
+    """generate()'s <|im_end|> handling against outputs of the REAL reference (oracle/make_golden_stop.py):
+    'first' = <|im_end|> as the prefill's token is not tested, the loop stops on the next one (inference.py:336-352,
+    :233); 'mid' = a sampled run (same torch RNG stream) that draws <|im_end|> a few frames in and stops there."""
+    from oracle import lm_oracle as O
+    from tests.lm_util import make_prompt
+
+    z = np.load(GOLD / "ref_stop_cases.npz")
+    cfg = O.tiny_config()
+    w = O.make_weights(cfg, seed=int(z["weight_seed"]), head_gain=float(z["head_gain"]))
+    w["embeddings.weight"][cfg.im_end_id] = (w["embeddings.weight"][int(z[f"{tag}_src_token"])].float()
+                                             * float(z[f"{tag}_gain"])).bfloat16()
+    prompt = torch.from_numpy(z["prompt"])
+    assert torch.equal(prompt, make_prompt(cfg, int(z["weight_seed"]), prompt.shape[1]))
+    ref = torch.from_numpy(z[f"{tag}_ref_tokens"])
+    torch.manual_seed(int(z[f"{tag}_rng_seed"]))
+    got = O.generate(O.setup(cfg, w), prompt, int(z["max_new_tokens"]), temperature=float(z[f"{tag}_temperature"]),
+                     top_p=float(z[f"{tag}_top_p"]), top_k=int(z[f"{tag}_top_k"]))
+    assert torch.equal(got.to(torch.int32), ref)
+    T = prompt.shape[1]
+    hits = (ref[0, T:] == cfg.im_end_id).nonzero().flatten().tolist()
+    assert ref.shape[1] < T + int(z["max_new_tokens"]) and ref[0, -1].item() == cfg.im_end_id
+    assert hits == ([0, 1] if tag == "first" else [ref.shape[1] - T - 1])
