@@ -284,3 +284,82 @@ def test_continuous_batcher_host_logic():
         b2.submit(mk(3, n, tag))
     b2.run()
     assert eng2.prefills == [[0, 1], [0, 1]]  # the short request's slot was not refilled on its own
+
+
+class _FakeCodec:
+    """encode() of a DAC: codes[b, c, t] = c + 10 * (sample count of clip b) for t < ceil(len / hop)."""
+    sample_rate, hop = 100, 10
+    device = torch.device("cpu")
+
+    def __init__(self):
+        self.batches = []
+
+    def encode(self, audios, lengths):
+        B, _, N = audios.shape
+        self.batches.append((B, N, lengths.tolist()))
+        T = -(-N // self.hop)
+        codes = torch.arange(3).view(1, 3, 1).expand(B, 3, T) + 10 * lengths.view(B, 1, 1)
+        return codes.to(torch.int64), -(-lengths // self.hop)
+
+
+def _write_wav(path, n, sr=100, nch=1):
+    import wave
+
+    with wave.open(str(path), "wb") as f:
+        f.setnchannels(nch)
+        f.setsampwidth(2)
+        f.setframerate(sr)
+        f.writeframes((np.arange(n * nch) % 100).astype("<i2").tobytes())
+
+
+def test_bulk_encode_pipeline(tmp_path, monkeypatch):
+    """fish_speech_b200/bulk_encode.py (the job of tools/vqgan/extract_vq.py): shard stride, skip of finished files,
+    length-grouped padded batches, per-file trimming of the codes, unreadable files skipped, stereo down-mix."""
+    from fish_speech_b200 import bulk_encode as be
+
+    lens = [95, 12, 40, 41, 230, 13, 39, 11]
+    for i, n in enumerate(lens):
+        _write_wav(tmp_path / f"a{i}.wav", n, nch=2 if i == 2 else 1)
+    (tmp_path / "broken.wav").write_bytes(b"not a wav")
+    (tmp_path / "notes.txt").write_text("x")
+    np.save(tmp_path / "a1.npy", np.zeros((3, 2)))  # already done -> skipped
+    files = be.list_audio_files(tmp_path)
+    assert [f.name for f in files] == sorted([f"a{i}.wav" for i in range(8)] + ["broken.wav"])
+
+    monkeypatch.setenv("SLURM_PROCID", "1")
+    monkeypatch.setenv("SLURM_NTASKS", "2")
+    assert be.worker_identity() == (1, 2)
+    todo_all = be.pending_files(files, 0, 1)
+    assert tmp_path / "a1.wav" not in todo_all and len(todo_all) == 8
+    assert be.pending_files(files, 1, 2) == todo_all[1::2]
+
+    # batch planning: similar lengths share a batch, caps respected, every index exactly once
+    plan = be.plan_batches([95, 40, 41, 230, 13, 39, 11], batch_size=3, max_padded_samples=300)
+    assert sorted(i for b in plan for i in b) == list(range(7))
+    assert all(len(b) <= 3 for b in plan) and [3] in plan  # the 230-sample clip cannot share a 300-sample budget
+    assert any(set(b) == {1, 2, 5} or set(b) >= {1, 2} for b in plan)
+
+    codec = _FakeCodec()
+    n, secs = be.encode_files(todo_all, codec, batch_size=3, max_batch_seconds=3.0)
+    assert n == 7 and abs(secs - sum(lens[i] for i in (0, 2, 3, 4, 5, 6, 7)) / 100) < 1e-6  # broken.wav skipped
+    for i in (0, 2, 3, 4, 5, 6, 7):
+        got = np.load(tmp_path / f"a{i}.npy")
+        assert got.shape == (3, -(-lens[i] // 10)) and got.dtype == np.int64
+        assert (got[:, 0] == np.arange(3) + 10 * lens[i]).all()  # its own codes, trimmed to its own length
+    assert np.load(tmp_path / "a1.npy").shape == (3, 2)  # untouched
+    assert not (tmp_path / "broken.npy").exists() and not list(tmp_path.glob("*.tmp"))
+    assert all(B <= 3 and B * N <= 300 for B, N, _ in codec.batches)
+    # everything is done now: a second pass finds nothing
+    assert be.pending_files(be.list_audio_files(tmp_path), 0, 1) == [tmp_path / "broken.wav"]
+
+
+def test_extract_vq_spawn_plan():
+    import importlib.util
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("extract_vq", Path(__file__).resolve().parent.parent / "tools/vqgan/extract_vq.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    plan = mod.spawn_plan(4, ["0", "3"])
+    assert [p["CUDA_VISIBLE_DEVICES"] for p in plan] == ["0", "3", "0", "3"]
+    assert [p["SLURM_PROCID"] for p in plan] == ["0", "1", "2", "3"] and {p["SLURM_NTASKS"] for p in plan} == {"4"}
