@@ -245,6 +245,9 @@ struct ConvKey {
     bool operator<(const ConvKey& o) const { return memcmp(this, &o, sizeof(ConvKey)) < 0; }
 };
 std::map<ConvKey, GemmPlan> g_conv_plans;
+// Plans are keyed by operand pointers and shapes; a long-running server that sees many distinct lengths (or whose
+// workspaces are re-allocated) would otherwise grow this map without bound. Tiled plans own no device memory.
+constexpr size_t kMaxConvPlans = 8192;
 std::mutex g_conv_mutex;
 
 }  // namespace
@@ -298,6 +301,7 @@ int fsb_conv_gemm(const void* d_x, int B, int T_in, int C_in, int row_stride, lo
             FSB_TRY(gemm_init());
             FSB_TRY(gemm_plan_init(&np, A, Bw, bn, bn == 128 ? 3 : 4, cdiv(T_out, 128), cdiv(C_out, bn), B));
             FSB_TRY(gemm_plan_tiled(&np, cdiv(T_out, 128), cdiv(C_out, bn), B, two));
+            if (g_conv_plans.size() >= kMaxConvPlans) g_conv_plans.clear();
             it = g_conv_plans.emplace(key, np).first;
         }
         plan = it->second;
@@ -345,6 +349,7 @@ int fsb_linear_f32(const void* d_x, int rows, int K, const void* d_w, int N, flo
             np.p.b_hint = kEvictNormal;
             FSB_TRY(gemm_init());
             FSB_TRY(gemm_plan_init(&np, A, Bx, 128, 4, cdiv(N, 128), cdiv(rows, 128), 1));
+            if (g_conv_plans.size() >= kMaxConvPlans) g_conv_plans.clear();
             it = g_conv_plans.emplace(key, np).first;
         }
         plan = it->second;

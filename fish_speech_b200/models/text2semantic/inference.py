@@ -461,11 +461,13 @@ def serve_requests(model, input_queue: "queue.Queue", max_slots: int, frames_per
     if batcher is None:
         batcher = ContinuousBatcher(model, max_slots=max_slots, frames_per_poll=frames_per_poll)
     live = 0  # plans not yet exhausted
+    waiting_queues: dict = {}  # id(plan) -> response queue of every plan that has a generate call in flight
     closing = False
 
     def advance(plan, response_queue, reply):
         """Run a plan until it asks for the next `generate` (submitted to the batcher) or ends."""
         nonlocal live
+        waiting_queues.pop(id(plan), None)
         try:
             while True:
                 kind, payload = plan.send(reply)
@@ -480,6 +482,7 @@ def serve_requests(model, input_queue: "queue.Queue", max_slots: int, frames_per
                     temperature=payload["temperature"], top_p=payload["top_p"], top_k=payload["top_k"],
                     seed=_next_seed(model),
                     on_done=lambda r, plan=plan, q=response_queue: advance(plan, q, r.result)))
+                waiting_queues[id(plan)] = response_queue
                 return
         except StopIteration:
             live -= 1
@@ -510,7 +513,14 @@ def serve_requests(model, input_queue: "queue.Queue", max_slots: int, frames_per
                 advance(plan, item.response_queue, None)
             if live == 0 and closing:
                 return
-            batcher.step()
+            try:
+                batcher.step()
+            except Exception as e:
+                # an engine failure ends the worker: every request in flight hears about it instead of hanging
+                logger.error(traceback.format_exc())
+                for q_ in waiting_queues.values():
+                    q_.put(WrappedGenerateResponse(status="error", response=e))
+                raise
     finally:
         batcher.close()
 

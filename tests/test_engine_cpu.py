@@ -363,3 +363,26 @@ def test_extract_vq_spawn_plan():
     plan = mod.spawn_plan(4, ["0", "3"])
     assert [p["CUDA_VISIBLE_DEVICES"] for p in plan] == ["0", "3", "0", "3"]
     assert [p["SLURM_PROCID"] for p in plan] == ["0", "1", "2", "3"] and {p["SLURM_NTASKS"] for p in plan} == {"4"}
+
+
+def test_slot_scheduler_worker_reports_engine_failure(monkeypatch):
+    """If the batcher itself fails (a CUDA error, say) every request in flight receives an error response and the
+    worker loop ends instead of leaving callers blocked on their queues."""
+    import queue as Q
+
+    monkeypatch.setattr(inf, "_generate_long_plan", _fake_plan)
+
+    class Boom(_FakeBatcher):
+        def step(self):
+            raise RuntimeError("device lost")
+
+    fb = Boom(slots=2)
+    q, outs = Q.Queue(), [Q.Queue(), Q.Queue()]
+    for rq in outs:
+        q.put(inf.GenerateRequest(request=dict(text="ab", chunks=1), response_queue=rq))
+    with pytest.raises(RuntimeError):
+        inf.serve_requests(_FakeModel(), q, 2, batcher=fb)
+    assert fb.closed
+    for rq in outs:
+        item = rq.get_nowait()
+        assert item.status == "error" and "device lost" in str(item.response)
