@@ -11,8 +11,9 @@ once the codec stage is present in this build; `config.stages` says which stages
 Prints ONE JSON line.  `value` = audio-seconds generated per second (whole job, all GPUs) with the prompts
 resident in HBM; `e2e` = the same through the public API (`generate_batch`) from pinned host memory,
 including H2D of the prompts and D2H of the generated codes; `roofline` = measured HBM stream of the
-dominant kernel (the tcgen05 weight-streaming GEMM) against MEASURED_PEAKS.json; `cpu_baseline` = the
-oracle port of the reference's CPU path timed on this box's host cores on a bounded sample.
+dominant kernel (the tcgen05 weight-streaming step GEMM) against MEASURED_PEAKS.json, in the frame and as a
+GEMM-only replay; `cpu_baseline` = the reference's CPU path (oracle/cpu_baseline.py) timed on this box's host
+cores on a bounded sample.
 
 Under torchrun (N > 1) every rank runs a full replica on its own shard of utterances (32 per GPU, weak
 scaling, no collective on the data path); times are device-side, max over ranks.
@@ -119,7 +120,7 @@ class ClockSampler:
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r01_gemm32_ncu_full.json); None if no capture is committed."""
+    `ncu --set full` capture (profiles/r02_step_gemm_ncu_full.json); None if no capture is committed."""
     try:
         d = json.loads((ROOT / "profiles" / "r01_gemm32_ncu_full.json").read_text())
         return d["avg_dram_bytes_per_launch"]
@@ -134,56 +135,12 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def usable_cores() -> int:
-    """Host cores this process can really use: the affinity mask capped by the cgroup CPU quota (GPU
-    boxes expose 128 hardware threads but a quota of 16; an oversized OpenMP team thrashes)."""
-    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    try:
-        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
-        if q != "max":
-            n = max(1, min(n, int(int(q) / int(p))))
-    except Exception:
-        pass
-    return n
+def cpu_reference(steps: int, warmup: int):
+    """The reference's own CPU implementation of the path on this box's host cores (oracle/cpu_baseline.py:
+    the unmodified reference modules when /root/reference exists, else the pinned oracle port)."""
+    from oracle import cpu_baseline
 
-
-def cpu_reference_port(steps: int, warmup: int, frames_per_step: int = 4):
-    """The reference's CPU path (oracle port: same operator sequence on CPU tensors) on the host cores,
-    on a bounded sample of the workload: ONE utterance (the reference is batch-1), 64-token prefill +
-    `frames_per_step` decode frames per step, bf16, all host threads.  Layer weights are ALIASED (every
-    layer shares one seeded tensor set: 0.2 GB >> L3, so the DRAM streaming cost per layer is intact)
-    to keep host RAM and set-up time bounded; timing does not depend on the weight values."""
-    from oracle import lm_oracle as O
-
-    cores = usable_cores()
-    torch.set_num_threads(cores)
-    cfg = O.LMConfig(max_seq_len=512)
-    one = O.LMConfig(max_seq_len=512, n_layer=1, n_fast_layer=1)
-    w1 = O.make_weights(one, seed=1234, head_gain=4.0)
-    w = dict(w1)
-    for l in range(cfg.n_layer):
-        for k, v in w1.items():
-            if k.startswith("layers.0."):
-                w[k.replace("layers.0.", f"layers.{l}.")] = v
-    for l in range(cfg.n_fast_layer):
-        for k, v in w1.items():
-            if k.startswith("fast_layers.0."):
-                w[k.replace("fast_layers.0.", f"fast_layers.{l}.")] = v
-    st = O.setup(cfg, w)
-    prompt = make_prompts(cfg, 1, 42)[0].long()
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        O.generate(st, prompt, frames_per_step + 1, temperature=0.7, top_p=0.7, top_k=1, noise=False,
-                   stop_on_im_end=False)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    frames = frames_per_step + 1
-    sec = sum(times) / len(times)
-    value = frames * FRAME / SR / sec
-    return value, sec, cores, (f"1 utterance (reference is batch-1): 64-token prefill + {frames} frames per step, bf16, "
-                               f"{cores} threads, layer weights aliased; audio-s/s = frames*2048/44100/time")
+    return cpu_baseline.measure(steps, warmup)
 
 
 def voice_clone_bench(args):
@@ -361,14 +318,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        v, sec, cores, sample = cpu_reference_port(max(1, min(args.steps, 3)), min(args.warmup, 1))
+        r = cpu_reference(args.steps, args.warmup)
+        cb = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps({
-            "impl": "reference", "metric": "audio-sec/s", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "impl": "reference", "metric": "audio-sec/s", "value": r["value"], "unit": "audio-s/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample},
-            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": {"workload": workload, "stages": ["lm_prefill", "lm_decode", "codec_decode"],
+                       "sampling": "greedy top_k=1 T=0.7 top_p=0.7",
+                       "step": "bounded sample of the workload, see cpu_baseline.sample",
+                       "t_prefill_s": r["t_prefill_s"], "t_frame_s": r["t_frame_s"], "t_codec_s": r["t_codec_s"],
+                       "frames_per_step": r["frames_per_step"], "codec_frames_per_step": r["codec_frames_per_step"]},
+            "cpu_baseline": cb,
+            "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
 
@@ -385,8 +347,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     cfg = s2pro_cfg()
     B, NF = args.batch, args.frames
@@ -475,6 +435,15 @@ def main():
     e2e_value = audio_s / (ms_e2e / 1e3)
     h2d = sum(p.numel() * p.element_size() for p in prompts_host) * world
     d2h = B * world * (cfg.num_codebooks + 1) * NF * 4 if args.no_codec else B * world * NF * FRAME * 4
+    # ---- stage breakdown: prefill alone, decode frames alone (device-timed, same inputs) ----
+    def prefill_only():
+        eng.reset()
+        eng.prefill(prompts_dev, list(range(B)), sp, do_sample=True)
+
+    prefill_only()
+    prefill_ms = timed(prefill_only, 3) / 3
+    DEC_FRAMES = min(NF - 1, 128)
+    decode_ms = timed(lambda: eng.decode(B, DEC_FRAMES, sp, use_graph=True), 1) / DEC_FRAMES  # per frame, context ~T+64
     codec = None
     if not args.no_codec:
         codec_stage()
@@ -482,7 +451,10 @@ def main():
         flops = 2.0 * codec_decode_macs(ccfg, NF) * B
         codec = {"ms": codec_ms, "tflops": flops / (codec_ms / 1e3) / 1e12, "flop_per_step": flops}
 
-    # ---- roofline of the dominant kernel: the decode GEMM stream, measured live ----
+    # ---- roofline of the dominant kernel (the weight-streaming step GEMM), measured live two ways:
+    #  in-frame  = algorithmic bytes of one decode frame / device time of one decode frame of the timed run
+    #              (everything between the GEMMs -- attention, sampling, dependency latency -- counts against it)
+    #  replay    = the same 311 step GEMMs launched back to back without the kernels in between ----
     import ctypes as C
 
     wb, nl = C.c_double(), C.c_int()
@@ -496,7 +468,9 @@ def main():
     kv_per_tok = cfg.n_layer * 2 * cfg.n_local_heads * cfg.head_dim * 2
     avg_L = T_PROMPT + NF / 2
     frame_bytes = wb.value + B * avg_L * kv_per_tok
-    frame_ms = ms_per_step / NF  # includes the prefill, amortised
+    frame_ms = ms_per_step / NF  # includes the prefill and the codec, amortised
+    dec_bytes = wb.value + B * (T_PROMPT + DEC_FRAMES / 2) * kv_per_tok
+    dec_gbs = dec_bytes / (decode_ms / 1e3) / 1e9
 
     out = None
     if rank == 0:
@@ -508,20 +482,25 @@ def main():
                 "workload": workload, "stages": stages, "utterances": B * world,
                 "frames_per_s": B * world * NF / (ms_per_step / 1e3),
                 "codec_tokens_per_s": B * world * NF * cfg.num_codebooks / (ms_per_step / 1e3),
-                "ms_per_frame": frame_ms, "sampling": "greedy top_k=1 T=0.7 top_p=0.7",
+                "ms_per_frame": frame_ms, "ms_per_decode_frame": decode_ms, "prefill_ms": prefill_ms,
+                "codec_ms": codec["ms"] if codec else None, "sampling": "greedy top_k=1 T=0.7 top_p=0.7",
                 "l2_note": "inputs larger than L2: 9.1 GB of weights streamed per frame (126 MB L2)",
                 "parallelism": f"replica x{world}, utts[rank::world]",
-                "frame_hbm_frac": frame_bytes / (frame_ms / 1e3) / 1e9 / pk["hbm_gbs"],
+                "step_hbm_frac": frame_bytes / (frame_ms / 1e3) / 1e9 / pk["hbm_gbs"],
             },
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "roofline": {
-                "bound": "hbm", "achieved": gemm_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": gemm_gbs / pk["hbm_gbs"], "traffic": ncu_traffic(), "peak_kind": pk_kind,
-                "kernel": "gemm_tc_kernel<32> (tcgen05 + TMA weight streaming, stream-K)",
-                "bytes_per_launch": wb.value / nl.value, "launches": nl.value * reps,
-                "avg_launch_us": gemm_ms * 1e3 / (nl.value * reps),
+                "bound": "hbm", "achieved": dec_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": dec_gbs / pk["hbm_gbs"], "traffic": ncu_traffic(), "peak_kind": pk_kind,
+                "kernel": "step_gemm_kernel (tcgen05 + TMA weight streaming, stream-K with in-kernel fix-up and fused "
+                          "epilogues), in-frame: bytes of one decode frame (weights + KV) / device time of one frame",
+                "bytes_per_launch": dec_bytes / nl.value, "launches_per_frame": nl.value,
+                "avg_launch_us": decode_ms * 1e3 / nl.value, "frame_bytes": dec_bytes, "frame_ms": decode_ms,
+                "replay": {"achieved": gemm_gbs, "frac": gemm_gbs / pk["hbm_gbs"], "bytes_per_launch": wb.value / nl.value,
+                           "launches": nl.value * reps, "avg_launch_us": gemm_ms * 1e3 / (nl.value * reps),
+                           "note": "the same step GEMMs back to back, no attention / sampling kernels between them"},
             },
             "clocks": clk,
         }
@@ -536,8 +515,8 @@ def main():
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:  # reported at N=1 only (rank 0's host cores)
             try:
-                v, sec, cores, sample = cpu_reference_port(1, 0, frames_per_step=3)
-                out["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample}
+                r = cpu_reference(3, 1)
+                out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:  # pragma: no cover
                 out["cpu_baseline"] = {"value": None, "error": repr(e)}
         print(json.dumps(out))

@@ -430,9 +430,8 @@ int fsb_resid_scale_norm(const float* d_y, int ld, const void* d_scale, const vo
                          const void* d_norm_w, void* d_n_out, int rows, int D, float eps, int round_bf16,
                          void* stream) {
     ResidNormArgs a{};
-    a.parts.ws = d_y;
-    a.parts.ld = ld;
-    a.parts.max_parts = 1;
+    a.y = d_y;
+    a.ld = ld;
     a.scale = reinterpret_cast<const bf16*>(d_scale);
     a.x_in = reinterpret_cast<const bf16*>(d_x_in);
     a.x_out = reinterpret_cast<bf16*>(d_x_out);
@@ -448,8 +447,8 @@ int fsb_resid_scale_norm(const float* d_y, int ld, const void* d_scale, const vo
 int fsb_qkv_rope(const float* d_qkv, int rows, int H, int Hkv, int Dh, const void* d_freqs, const int32_t* d_row_seq,
                  const int32_t* d_row_pos, void* d_q, void* d_k, void* d_v, int S, void* stream) {
     QkvPrepArgs a{};
-    a.parts.ws = d_qkv;
-    a.parts.ld = (H + 2 * Hkv) * Dh;
+    a.y = d_qkv;
+    a.ld = (H + 2 * Hkv) * Dh;
     a.freqs = reinterpret_cast<const bf16*>(d_freqs);
     a.row_seq = d_row_seq;
     a.row_pos = d_row_pos;
@@ -480,8 +479,8 @@ int fsb_window_attn(const void* d_q, const void* d_k, const void* d_v, const int
 
 int fsb_swiglu_f32(const float* d_y, int rows, int I, void* d_h, void* stream) {
     SwigluArgs a{};
-    a.parts.ws = d_y;
-    a.parts.ld = 2 * I;
+    a.y = d_y;
+    a.ld = 2 * I;
     a.h = reinterpret_cast<bf16*>(d_h);
     a.rows = rows;
     a.I = I;

@@ -266,47 +266,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// Device-side dependency flags (decode chain): a kernel publishes "my outputs are written" with a release
-// increment; its consumer spins with acquire loads instead of waiting for the whole grid to complete.
-struct DepFlag {
-    unsigned* ctr;    // null => use griddepcontrol.wait / no signal
-    unsigned target;  // value at which the dependency is satisfied
-};
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_release_gpu(unsigned* p) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
-}
-__device__ __forceinline__ void flag_wait(const DepFlag& f) {
-    if (ld_acquire_gpu(f.ctr) >= f.target) return;
-    const long long t0 = clock64();
-    while (ld_acquire_gpu(f.ctr) < f.target) {
-        if (clock64() - t0 > 4000000000ll) {
-            printf("fsb: dependency flag timeout block=%d have=%u want=%u\n", blockIdx.x, ld_acquire_gpu(f.ctr), f.target);
-            __trap();
-        }
-    }
-}
-// Kernel prologue for a consumer: either the classic grid dependency or the flag (thread 0 spins, CTA syncs).
-__device__ __forceinline__ void dep_wait_cta(const DepFlag& f) {
-    if (f.ctr == nullptr) {
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        return;
-    }
-    if (threadIdx.x == 0) flag_wait(f);
-    __syncthreads();
-}
-// Kernel epilogue for a producer of a flag: all threads' global writes, then ONE release increment per CTA.
-__device__ __forceinline__ void dep_signal_cta(unsigned* ctr) {
-    if (ctr == nullptr) return;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) red_release_gpu(ctr);
-}
-
 // Programmatic dependent launch: wait for the producing grid / allow the dependent grid to start.
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;

@@ -165,9 +165,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned long long* trace =
-        p.trace ? p.trace + (static_cast<size_t>(p.trace_id) * gridDim.x + blockIdx.x) * 3 : nullptr;
-    if (trace && threadIdx.x == 0) trace[0] = globaltimer_ns();
 
     // Work items of this CTA: a stream-K range (several segments, each of one output tile), a range of
     // the persistent tiled schedule, or the single tile named by blockIdx.
@@ -236,7 +233,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int it = 0;
             int pre = 0;  // ring slots whose A tile was requested early
-            bool waited = false;
             if (p.a_static) {
                 int n = item_begin, kb = 0, i0 = 0, j0 = 0, kb0 = 0, kb1 = 0, slot = 0;
                 if (n < item_end) {
@@ -272,15 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
-            if (p.b_ready.ctr != nullptr) {
-                flag_wait(p.b_ready);
-                asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores of another grid -> TMA reads
-            } else {
-                pdl_wait();
-            }
-            if (trace) trace[1] = globaltimer_ns();
-            waited = true;
-            (void)waited;
+            pdl_wait();
             for (int n = item_begin; n < item_end; ++n) {
                 int i0, j0, kb0, kb1, slot;
                 get_item(n, i0, j0, kb0, kb1, slot);
@@ -381,17 +369,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8u * a);
         }
-        if (MODE == 0 && p.done_ctr != nullptr) {
-            // publish this CTA's partial sums: every epilogue thread fences its stores, the epilogue warps
-            // meet on a named barrier, one thread does the release increment
-            __threadfence();
-            asm volatile("bar.sync 1, %0;" ::"n"(GemmRoles<MODE>::kEpiWarps * 32) : "memory");
-            if (threadIdx.x == 0) red_release_gpu(p.done_ctr);
-        }
     }
     tc_fence_before();
     __syncthreads();
-    if (trace && threadIdx.x == 0) trace[2] = globaltimer_ns();
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -418,7 +398,9 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int make_tmap(CUtensorMap* tm, const GemmOperand& op, int box_rows) {
+}  // namespace
+
+int gemm_make_tmap(CUtensorMap* tm, const GemmOperand& op, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return 1;
     FSB_CHECK((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0, "TMA operand not 16-byte aligned");
@@ -444,6 +426,8 @@ int make_tmap(CUtensorMap* tm, const GemmOperand& op, int box_rows) {
     return 0;
 }
 
+namespace {
+
 template <int BN, int MODE>
 int launch_bn_mode(const GemmPlan& plan, cudaStream_t stream) {
     auto k = gemm_tc_kernel<BN, MODE>;
@@ -466,8 +450,8 @@ int launch_bn(const GemmPlan& plan, cudaStream_t stream) {
 int gemm_plan_init(GemmPlan* plan, const GemmOperand& A, const GemmOperand& B, int bn, int stages,
                    int tiles_i, int tiles_j, int batch) {
     FSB_CHECK(bn == 32 || bn == 64 || bn == 128 || bn == 192 || bn == 256, "unsupported BN %d", bn);
-    FSB_TRY(make_tmap(&plan->tmA, A, kBlockM));
-    FSB_TRY(make_tmap(&plan->tmB, B, bn));
+    FSB_TRY(gemm_make_tmap(&plan->tmA, A, kBlockM));
+    FSB_TRY(gemm_make_tmap(&plan->tmB, B, bn));
     const int stage_bytes = kATileBytes + bn * kBlockK * 2;
     const int max_stages = (227 * 1024 - 1024 - 256) / stage_bytes;
     if (stages > max_stages) stages = max_stages;
@@ -564,7 +548,9 @@ int gemm_init() {
     // attribute call is needed later (e.g. while a stream is being captured into a CUDA graph)
 #define FSB_GEMM_ATTR(BN_, M_)                                                                       \
     FSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  227 * 1024));
+                                  227 * 1024));                                                        \
+    FSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN_, M_>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                  cudaSharedmemCarveoutMaxShared));
     FSB_GEMM_ATTR(32, 0) FSB_GEMM_ATTR(64, 0) FSB_GEMM_ATTR(128, 0) FSB_GEMM_ATTR(256, 0)
     FSB_GEMM_ATTR(32, 1) FSB_GEMM_ATTR(64, 1) FSB_GEMM_ATTR(128, 1) FSB_GEMM_ATTR(256, 1)
     FSB_GEMM_ATTR(192, 0) FSB_GEMM_ATTR(192, 1)

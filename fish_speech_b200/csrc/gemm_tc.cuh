@@ -31,10 +31,6 @@ struct GemmParams {
     int stages;
     int a_static;  // operand A is constant data (weights): prefetch it before griddepcontrol.wait
     int l2_prefetch;  // extra k-blocks of A per CTA prefetched into L2 before the wait
-    DepFlag b_ready;     // optional: activations (operand B) are published by this flag instead of grid completion
-    unsigned* done_ctr;  // optional: incremented once per CTA when its partials are written (MODE 0)
-    unsigned long long* trace;  // optional [launch][cta][3] globaltimer: start, after dependency wait, end
-    int trace_id;
     // ---- work decomposition ----
     const int4* sched;     // optional items {tile_i | tile_j<<16, kb_begin, kb_end, slot}; else blockIdx
     const int* cta_items;  // [grid.x + 1] item range of each CTA (stream-K)
@@ -92,5 +88,7 @@ int gemm_plan_tiled(GemmPlan* plan, int tiles_i, int tiles_j, int batch, int cta
 void gemm_plan_free(GemmPlan* plan);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 int gemm_init();  // set kernel attributes (idempotent)
+// 3-D {k, rows, batch} bf16 tensor map with the 128-byte swizzle and a {64, box_rows, 1} box.
+int gemm_make_tmap(CUtensorMap* tm, const GemmOperand& op, int box_rows);
 
 }  // namespace fsb

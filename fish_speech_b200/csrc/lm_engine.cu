@@ -2,12 +2,18 @@
 // prefill / per-frame decode as a fixed kernel sequence (captured into a CUDA graph for decode).
 //
 // HBM layout (all bf16 unless noted)
-//   weights            caller-owned, row-major [out, in] as in the checkpoint (TMA-ready, K-major)
+//   weights            caller-owned, row-major [out, in] as in the checkpoint (TMA-ready, K-major); the fused
+//                      w1|w3 matrix has its rows interleaved per 128-row tile (lm_gemm.cuh, w13_gate_row)
 //   slow KV cache      [n_layer][max_batch][Hkv][kv_len][Dh]   x2 (K, V)
 //   fast KV cache      [n_fast_layer][max_batch][fHkv][num_codebooks][fDh]  x2
-//   decode workspaces  xres_d/xn_d [32][max(D,Df)], q_d/attn_d [32][max(H*Dh)], h_d [32][max(I)]
-//   prefill workspaces same with max_rows rows
-//   ws                 fp32 GEMM partial sums: [slot][row][feature]
+//   decode state       residual streams x_slow / x_fast [32][D] + their per-128-feature sums of squares
+//                      (fp32 [32][32]); q / attention / SwiGLU operands [32][*]; logits fp32 [32][n]
+//   step_ws            fp32 stream-K partials of the step GEMMs: [slot][tile][128][32]
+//   prefill workspaces [max_rows][*] operands + ws fp32 [max_rows][N]
+//
+// One decode frame (inference.py:96-181) = embed, 36 x {qkv GEMM (norm on load; bias / qk-norm / RoPE / KV append
+// in the epilogue), attention, wo GEMM (+residual), w1|w3 GEMM (norm on load; SwiGLU in the epilogue), w2 GEMM
+// (+residual)}, head GEMM + sampler, then 10 fast passes of 4 such layers each: ~410 kernels, five per layer.
 //
 // Reference: fish_speech/models/text2semantic/llama.py:390-466 (slow step), :799-817 (fast step),
 // fish_speech/models/text2semantic/inference.py:96-181 (one frame), :184-238 (frame loop).
@@ -20,47 +26,45 @@
 
 #include "../../include/fishb200.h"
 #include "gemm_tc.cuh"
+#include "lm_gemm.cuh"
 #include "lm_kernels.cuh"
-#include "lm_persist.cuh"
 
 using namespace fsb;
 
 namespace {
 
 typedef __nv_bfloat16 bf16;
-constexpr int kDecRows = 32;  // decode GEMM N tile: up to 32 sequences per step
+constexpr int kDecRows = kStepRows;  // decode GEMM N tile: up to 32 sequences per step
 
 struct LayerW {
     const bf16 *attn_norm, *wqkv, *bqkv, *q_norm, *k_norm, *wo, *bo, *ffn_norm, *w13, *w2;
 };
-struct LayerPlans {
+struct StepLayer {
+    StepGemmPlan qkv, wo, w13, w2;
+};
+struct PrefillLayer {
     GemmPlan qkv, wo, w13, w2;
 };
 
 struct Stack {
     int D = 0, H = 0, Hkv = 0, Dh = 0, I = 0, nl = 0, S = 0;
+    int n13 = 0;  // rows of the interleaved w1|w3 matrix: ceil(I / 64) * 128
     bool qk_norm = false;
     int bf16_math = 0;
     std::vector<LayerW> w;
-    std::vector<LayerPlans> dec;  // BN=32, stream-K, B operand = decode workspaces
-    std::vector<LayerPlans> pf;   // BN=128 tiles, B operand = prefill workspaces (slow only)
-    std::vector<LayerPlans> pk;   // stream-K over one CTA per SM, for the persistent stack kernel
-    PkLayer* pk_layers = nullptr;  // device array
+    std::vector<StepLayer> dec;     // decode: fused step GEMMs
+    std::vector<PrefillLayer> pf;   // prefill: BN=128 tiles, fp32 result + consumer kernels (slow only)
     bf16 *kcache = nullptr, *vcache = nullptr;
     const bf16* freqs = nullptr;
     size_t cache_layer_stride = 0;
+    bf16* xres = nullptr;  // decode residual stream [32][D]
+    float* ssq = nullptr;  // its per-tile sums of squares [32][kSsqStride]
 };
 
 }  // namespace
 
 struct fsb_lm {
-    // device-side dependency flags for the decode chain (FSB_FLAGS, see common.cuh DepFlag)
-    bool flags_on = false;
-    unsigned* flag_base = nullptr;
-    int flag_next = 0;
-    static constexpr int kFlagCap = 4096;
     // per-slot request control (continuous batching): see SlotCtl in lm_kernels.cuh
-    bool fused_fast_only = false;
     bool slot_control = false;
     int* slot_state = nullptr;
     int* slot_limit = nullptr;
@@ -71,37 +75,41 @@ struct fsb_lm {
     bool graph_slot_control = false;
     fsb_lm_config cfg;
     int num_sms = 148;
+    int step_ctas = 0, step_stages = 4;
     Stack slow, fast;
     const bf16 *emb = nullptr, *cb_emb = nullptr, *norm_w = nullptr, *head_w = nullptr;
     const bf16 *fast_emb = nullptr, *fast_norm_w = nullptr, *fast_out_w = nullptr;
     const bf16 *fast_proj_w = nullptr, *fast_proj_b = nullptr;
     int head_rows = 0;
-    GemmPlan head_plan, fast_out_plan, proj_plan;
+    StepGemmPlan head_plan, fast_out_plan, proj_plan;
     bool has_proj = false;
-    // workspaces
-    bf16 *xres_d = nullptr, *xn_d = nullptr, *q_d = nullptr, *attn_d = nullptr, *h_d = nullptr;
+    // decode workspaces
+    bf16 *q_d = nullptr, *attn_d = nullptr, *h_d = nullptr, *hid_d = nullptr;
+    float* logits_ws = nullptr;
+    int logits_ld = 0;
+    float* step_ws = nullptr;
+    size_t step_ws_floats = 0;
+    unsigned* tile_ctr = nullptr;
+    int tile_ctr_len = 0;
+    // prefill workspaces
     bf16 *xres_p = nullptr, *xn_p = nullptr, *q_p = nullptr, *attn_p = nullptr, *h_p = nullptr;
-    bf16* proj_d = nullptr;
     float* ws = nullptr;
     size_t ws_floats = 0;
     // state
     int *cur_tok = nullptr, *out_tokens = nullptr, *n_out = nullptr, *pos = nullptr, *finished = nullptr;
     int *ras_window = nullptr, *iota = nullptr, *fpos = nullptr;
     unsigned long long* step = nullptr;
-    // debug
+    // debug / test hooks
     float *slow_logits = nullptr, *fast_logits = nullptr;
-    bf16* dbg_x = nullptr;
+    const float* noise_u = nullptr;
+    int noise_draws = 0, noise_ld = 0;
     int ctx_lcap = 0;  // score-buffer bound for the slow attention (0 = capacity)
     int graph_lcap = -1;
-    bool persistent = false;
-    bool fused_prep_attn = false;
-    int pk_stages = 8;
-    unsigned* pk_bar = nullptr;
-    unsigned long long* pk_trace = nullptr;
     // decode graph cache
     cudaGraphExec_t graph_exec = nullptr;
     int graph_batch = -1;
     int graph_kernels = 0;  // kernels inside one captured frame
+    const float* graph_noise = nullptr;
     fsb_sampling graph_sampling{};
     std::vector<void*> owned;
     std::map<std::string, std::pair<void*, size_t>> named;
@@ -121,248 +129,57 @@ int dalloc(fsb_lm* h, T** p, size_t count, const char* name = nullptr) {
     return 0;
 }
 
-// Decode-orientation plan: A = weight [n_out, k] on the TMEM lanes, B = activations [rows, k].
-int make_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const bf16* act, int act_rows,
-              bool decode, int force_per_sm = 0) {
+// Prefill plan: A = weight [n_out, k] on the TMEM lanes, B = activations [rows, k], fp32 result ws[row][n_out].
+int make_prefill_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const bf16* act, int act_rows) {
     memset(plan, 0, sizeof(*plan));
     GemmOperand A{w, k, n_out, 1, k, static_cast<long long>(n_out) * k};
     GemmOperand B{act, k, act_rows, 1, k, static_cast<long long>(act_rows) * k};
     GemmParams& p = plan->p;
-    const int kblocks = cdiv(k, 64);
-    p.kb_per_tap = kblocks;
+    p.kb_per_tap = cdiv(k, 64);
     p.num_taps = 1;
-    p.a_hint = kEvictFirst;  // weights are streamed once per step (>> L2)
+    p.a_hint = kEvictNormal;
     p.a_static = 1;
-    {
-        const char* e = getenv("FSB_L2_PREFETCH");
-        p.l2_prefetch = decode ? (e ? atoi(e) : 0) : 0;
-    }
-    p.b_hint = kEvictLast;   // the activation tile is re-read by every CTA
+    p.b_hint = kEvictLast;
     p.rows_i = n_out;
     p.mode = 0;
     p.ws = h->ws;
     p.ws_ld = n_out;
-    const int tiles_i = cdiv(n_out, 128);
-    if (decode) {
-        // ring depth / CTAs per SM are tunable for experiments (FSB_STAGES, FSB_CTAS_PER_SM)
-        const char* es = getenv("FSB_STAGES");
-        const char* ec = getenv("FSB_CTAS_PER_SM");
-        const int stages = es ? atoi(es) : 4;   // measured best on B200: 4 stages x 2 CTAs per SM
-        const int per_sm = force_per_sm ? force_per_sm : (ec ? atoi(ec) : 2);
-        FSB_TRY(gemm_plan_init(plan, A, B, 32, stages, tiles_i, 1, 1));
-        p.rows_j = kDecRows;
-        p.ws_slot_stride = static_cast<long long>(kDecRows) * n_out;
-        // the persistent kernel indexes the schedule by blockIdx.x of a full grid: keep empty CTA ranges
-        FSB_TRY(gemm_plan_streamk(plan, tiles_i, kblocks, h->num_sms * per_sm, force_per_sm != 0));
-        FSB_CHECK(static_cast<size_t>(plan->max_parts) * kDecRows * n_out <= h->ws_floats,
-                  "partial workspace too small");
-    } else {
-        FSB_TRY(gemm_plan_init(plan, A, B, 128, 4, tiles_i, cdiv(act_rows, 128), 1));
-        p.rows_j = act_rows;
-        p.ws_slot_stride = 0;
-        FSB_CHECK(static_cast<size_t>(act_rows) * n_out <= h->ws_floats, "partial workspace too small");
-    }
+    FSB_TRY(gemm_plan_init(plan, A, B, 128, 4, cdiv(n_out, 128), cdiv(act_rows, 128), 1));
+    p.rows_j = act_rows;
+    p.ws_slot_stride = 0;
+    FSB_CHECK(static_cast<size_t>(act_rows) * n_out <= h->ws_floats, "prefill workspace too small");
     return 0;
 }
 
-Partials parts_of(const GemmPlan& p) {
-    Partials P;
-    P.ws = p.p.ws;
-    P.slot_stride = p.p.ws_slot_stride;
-    P.ld = p.p.ws_ld;
-    P.nparts = p.nparts_dev;
-    P.max_parts = p.max_parts;
-    return P;
-}
-
-// Every frame starts from zeroed counters; each dependency edge of the frame gets its own counter.
-int flags_begin(fsb_lm* h, cudaStream_t st) {
-    if (!h->flags_on) return 0;
-    h->flag_next = 0;
-    FSB_CUDA(cudaMemsetAsync(h->flag_base, 0, static_cast<size_t>(fsb_lm::kFlagCap) * 4, st));
-    return 0;
-}
-unsigned* flag_new(fsb_lm* h) {
-    if (!h->flags_on || h->flag_next >= fsb_lm::kFlagCap) return nullptr;
-    return h->flag_base + h->flag_next++;
-}
-
-// Decode GEMM with flag dependencies: operand B becomes valid when `ready` is satisfied; the returned
-// flag is satisfied when every CTA has written its partial sums.
-int launch_dec_gemm(fsb_lm* h, const GemmPlan& plan, const DepFlag& ready, DepFlag* done, cudaStream_t st) {
-    *done = DepFlag{nullptr, 0};
-    if (!h->flags_on) return gemm_launch(plan, st);
-    GemmPlan q = plan;
-    q.p.b_ready = ready;
-    q.p.done_ctr = flag_new(h);
-    if (q.p.done_ctr) *done = DepFlag{q.p.done_ctr, plan.grid.x * plan.grid.y * plan.grid.z};
+int launch_rows_of(const GemmPlan& plan, int rows, cudaStream_t st) {
+    GemmPlan q = plan;  // restrict the column tiles to the live rows
+    q.grid.y = cdiv(rows, plan.bn);
+    q.p.rows_j = rows;
     return gemm_launch(q, st);
 }
 
-int launch_rows(const GemmPlan& plan, int rows, cudaStream_t st) {
-    // prefill plans: restrict the column tiles to the live rows
-    if (plan.p.sched == nullptr) {
-        GemmPlan q = plan;
-        q.grid.y = cdiv(rows, plan.bn);
-        q.p.rows_j = rows;
-        return gemm_launch(q, st);
-    }
-    return gemm_launch(plan, st);
+// Step GEMM over the weight `w` [n_out, K]. act != null: operand X = act, used as it is; act == null: operand X = the
+// stack's residual stream, normalised on load (bind_norm_on_load supplies the norm).
+int make_step_plan(fsb_lm* h, StepGemmPlan* plan, int epi, const bf16* w, int n_out, int K, const bf16* act,
+                   const Stack* norm_of = nullptr) {
+    const bool norm = act == nullptr;
+    if (norm) act = norm_of->xres;
+    return step_plan_init(plan, epi, w, n_out, K, act, norm, h->step_ctas, h->step_stages, h->step_ws,
+                          h->step_ws_floats, h->tile_ctr, h->tile_ctr_len);
 }
 
-struct RowCtx {
-    int rows;
-    const int* row_seq;
-    const int* row_pos;
-    bf16 *xres, *xn, *q, *attn, *hbuf;
-    bool decode;
-};
+void bind_norm_on_load(StepGemmPlan* plan, const Stack& s, const bf16* norm_w, float eps) {
+    plan->p.x_ssq = s.ssq;
+    plan->p.norm_w = norm_w;
+    plan->p.x_nt = cdiv(s.D, 128);
+    plan->p.eps = eps;
+}
 
-// One transformer stack over `rows` token rows. On entry xn = attention_norm_0(xres).
-// `final_norm`: weight of the norm applied after the last layer (-> xn). `stop_after_kv`: fast pass 0
-// only needs the last layer's K/V (its logits are discarded, inference.py:147).
-int run_stack(fsb_lm* h, Stack& s, const RowCtx& c, const bf16* final_norm, bool stop_after_kv,
-              bf16* dbg, cudaStream_t st, DepFlag* ready_io = nullptr) {
-    const float eps = h->cfg.norm_eps;
-    // flag mode (decode only): `ready` = "xn holds this layer's normed input"
-    const bool fl = h->flags_on && c.decode && ready_io != nullptr && !h->persistent && !h->fused_prep_attn;
-    DepFlag ready = fl ? *ready_io : DepFlag{nullptr, 0};
-    DepFlag gd{nullptr, 0};
-    if (h->persistent && c.decode && s.pk_layers != nullptr) {
-        PkArgs A{};
-        A.layers = s.pk_layers;
-        A.nl = s.nl; A.rows = c.rows; A.D = s.D; A.H = s.H; A.Hkv = s.Hkv; A.Dh = s.Dh; A.I = s.I; A.S = s.S;
-        A.eps = eps;
-        A.bf16_math = s.bf16_math;
-        A.qk_norm = s.qk_norm ? 1 : 0;
-        A.kv_only_last = stop_after_kv ? 1 : 0;
-        A.stages = h->pk_stages;
-        {
-            const char* e = getenv("FSB_PK_L2PF");
-            A.l2_prefetch = e ? atoi(e) : 24;
-        }
-        A.row_seq = c.row_seq;
-        A.row_pos = c.row_pos;
-        A.freqs = s.freqs;
-        A.xres = c.xres; A.xn = c.xn; A.attn = c.attn; A.hbuf = c.hbuf;
-        A.ws = h->ws;
-        A.bar = h->pk_bar;
-        A.trace = (s.bf16_math == 0) ? h->pk_trace : nullptr;  // slow stack only
-        A.trace_max = 1024;
-        (void)final_norm;  // baked into the last layer's next_norm
-        return launch_stack_persistent(A, h->num_sms, st);
-    }
-    for (int l = 0; l < s.nl; ++l) {
-        const LayerW& w = s.w[l];
-        LayerPlans& P = c.decode ? s.dec[l] : s.pf[l];
-        if (fl) FSB_TRY(launch_dec_gemm(h, P.qkv, ready, &gd, st));
-        else FSB_TRY(launch_rows(P.qkv, c.rows, st));
-        if (c.decode && h->fused_prep_attn && (!h->fused_fast_only || s.bf16_math)) {
-            // decode rows: q/k/v post-processing, KV append and attention in one launch
-            PkArgs A{};
-            A.rows = c.rows; A.D = s.D; A.H = s.H; A.Hkv = s.Hkv; A.Dh = s.Dh; A.I = s.I; A.S = s.S;
-            A.eps = eps;
-            A.bf16_math = s.bf16_math;
-            A.qk_norm = s.qk_norm ? 1 : 0;
-            A.row_seq = c.row_seq;
-            A.row_pos = c.row_pos;
-            A.freqs = s.freqs;
-            A.attn = c.attn;
-            A.ws = h->ws;
-            PkLayer L{};
-            L.qkv.nparts = P.qkv.nparts_dev;
-            L.qkv.n_out = P.qkv.p.ws_ld;
-            L.qkv.max_parts = P.qkv.max_parts;
-            L.qkv.slot_stride = P.qkv.p.ws_slot_stride;
-            L.bqkv = w.bqkv;
-            L.q_norm = s.qk_norm ? w.q_norm : nullptr;
-            L.k_norm = s.qk_norm ? w.k_norm : nullptr;
-            L.kcache = s.kcache + l * s.cache_layer_stride;
-            L.vcache = s.vcache + l * s.cache_layer_stride;
-            const bool kv_only = stop_after_kv && l == s.nl - 1;
-            const int rc = launch_prep_attn(A, L, kv_only ? 1 : 0, st);
-            if (rc > 0) return rc;
-            if (rc == 0) {
-                if (kv_only) return 0;
-                goto after_attention;
-            }
-        }
-        {
-        QkvPrepArgs qa{};
-        qa.parts = parts_of(P.qkv);
-        qa.bias = w.bqkv;
-        qa.q_norm = s.qk_norm ? w.q_norm : nullptr;
-        qa.k_norm = s.qk_norm ? w.k_norm : nullptr;
-        qa.freqs = s.freqs;
-        qa.row_seq = c.row_seq;
-        qa.row_pos = c.row_pos;
-        qa.q = c.q;
-        qa.kcache = s.kcache + l * s.cache_layer_stride;
-        qa.vcache = s.vcache + l * s.cache_layer_stride;
-        qa.rows = c.rows; qa.H = s.H; qa.Hkv = s.Hkv; qa.Dh = s.Dh; qa.S = s.S;
-        qa.eps = eps;
-        qa.wait = gd;
-        FSB_TRY(launch_qkv_prep(qa, st));
-        if (stop_after_kv && l == s.nl - 1) {
-            if (ready_io) *ready_io = DepFlag{nullptr, 0};  // the next kernel depends on this grid classically
-            return 0;
-        }
-        AttnArgs aa{};
-        aa.q = c.q;
-        aa.kcache = qa.kcache;
-        aa.vcache = qa.vcache;
-        aa.row_seq = c.row_seq;
-        aa.row_pos = c.row_pos;
-        aa.out = c.attn;
-        aa.rows = c.rows; aa.H = s.H; aa.Hkv = s.Hkv; aa.Dh = s.Dh; aa.S = s.S;
-        aa.window = 0;
-        aa.lcap = (s.bf16_math == 0) ? h->ctx_lcap : 0;  // slow stack: bounded by the live context, not the capacity
-        aa.bf16_math = s.bf16_math;
-        aa.done_ctr = fl ? flag_new(h) : nullptr;
-        FSB_TRY(launch_attn(aa, st));
-        ready = DepFlag{aa.done_ctr, static_cast<unsigned>(s.Hkv * c.rows)};
-        }
-    after_attention:
-        if (fl) FSB_TRY(launch_dec_gemm(h, P.wo, ready, &gd, st));
-        else FSB_TRY(launch_rows(P.wo, c.rows, st));
-        ResidNormArgs r1{};
-        r1.parts = parts_of(P.wo);
-        r1.bias = w.bo;
-        r1.x_in = c.xres; r1.x_out = c.xres;
-        r1.norm_w = w.ffn_norm; r1.n_out = c.xn;
-        r1.rows = c.rows; r1.D = s.D; r1.eps = eps;
-        r1.wait = gd;
-        r1.done_ctr = fl ? flag_new(h) : nullptr;
-        FSB_TRY(launch_resid_norm(r1, st));
-        ready = DepFlag{r1.done_ctr, static_cast<unsigned>(c.rows)};
-        if (fl) FSB_TRY(launch_dec_gemm(h, P.w13, ready, &gd, st));
-        else FSB_TRY(launch_rows(P.w13, c.rows, st));
-        SwigluArgs sa{};
-        sa.parts = parts_of(P.w13);
-        sa.h = c.hbuf; sa.rows = c.rows; sa.I = s.I;
-        sa.wait = gd;
-        sa.done_ctr = fl ? flag_new(h) : nullptr;
-        FSB_TRY(launch_swiglu(sa, st));
-        ready = DepFlag{sa.done_ctr, static_cast<unsigned>(swiglu_ctas(c.rows, s.I))};
-        if (fl) FSB_TRY(launch_dec_gemm(h, P.w2, ready, &gd, st));
-        else FSB_TRY(launch_rows(P.w2, c.rows, st));
-        ResidNormArgs r2{};
-        r2.parts = parts_of(P.w2);
-        r2.x_in = c.xres; r2.x_out = c.xres;
-        r2.norm_w = (l + 1 < s.nl) ? s.w[l + 1].attn_norm : final_norm;
-        r2.n_out = c.xn;
-        r2.rows = c.rows; r2.D = s.D; r2.eps = eps;
-        r2.wait = gd;
-        r2.done_ctr = fl ? flag_new(h) : nullptr;
-        FSB_TRY(launch_resid_norm(r2, st));
-        ready = DepFlag{r2.done_ctr, static_cast<unsigned>(c.rows)};
-        if (dbg)
-            FSB_CUDA(cudaMemcpyAsync(dbg + static_cast<size_t>(l + 1) * kDecRows * s.D, c.xres,
-                                     static_cast<size_t>(std::min(c.rows, kDecRows)) * s.D * 2,
-                                     cudaMemcpyDeviceToDevice, st));
-    }
-    if (ready_io) *ready_io = ready;
-    return 0;
+void bind_resid(StepGemmPlan* plan, const Stack& s, const bf16* bias, bool add_residual) {
+    plan->p.bias = bias;
+    plan->p.resid = add_residual ? s.xres : nullptr;
+    plan->p.x_out = s.xres;
+    plan->p.ssq_out = s.ssq;
 }
 
 SlotCtl slot_ctl(const fsb_lm* h) {
@@ -378,24 +195,136 @@ SlotCtl slot_ctl(const fsb_lm* h) {
     return c;
 }
 
-// Head + sampling + fast passes + bookkeeping for `rows` sequences whose final-normed last hidden
-// state is in xn_d[0..rows) (and un-normed residual in xres_d). inference.py:114-181.
+// ---- decode: one transformer stack over the batch rows, five kernels per layer ----
+int run_stack_decode(fsb_lm* h, Stack& s, int rows, const int* row_seq, const int* row_pos, bool stop_after_kv,
+                     cudaStream_t st) {
+    auto launch = [&](const StepGemmPlan& plan) -> int {
+        StepGemmPlan q = plan;
+        q.p.rows = rows;
+        q.p.row_seq = row_seq;
+        q.p.row_pos = row_pos;
+        return step_gemm_launch(q, st);
+    };
+    for (int l = 0; l < s.nl; ++l) {
+        StepLayer& P = s.dec[l];
+        FSB_TRY(launch(P.qkv));
+        if (stop_after_kv && l == s.nl - 1) return 0;  // fast pass 0 only fills the KV cache (inference.py:147)
+        AttnArgs aa{};
+        aa.q = h->q_d;
+        aa.kcache = s.kcache + l * s.cache_layer_stride;
+        aa.vcache = s.vcache + l * s.cache_layer_stride;
+        aa.row_seq = row_seq;
+        aa.row_pos = row_pos;
+        aa.out = h->attn_d;
+        aa.rows = rows; aa.H = s.H; aa.Hkv = s.Hkv; aa.Dh = s.Dh; aa.S = s.S;
+        aa.window = 0;
+        aa.lcap = (s.bf16_math == 0) ? h->ctx_lcap : 0;  // slow stack: bounded by the live context, not the capacity
+        aa.bf16_math = s.bf16_math;
+        FSB_TRY(launch_attn(aa, st));
+        FSB_TRY(launch(P.wo));
+        FSB_TRY(launch(P.w13));
+        FSB_TRY(launch(P.w2));
+    }
+    return 0;
+}
+
+// ---- prefill: the same stack over `rows` token rows with wide-N tensor-core GEMMs and consumer kernels.
+// On entry xn_p = attention_norm_0(xres_p). ----
+int run_stack_prefill(fsb_lm* h, Stack& s, int rows, const int* row_seq, const int* row_pos, cudaStream_t st) {
+    const float eps = h->cfg.norm_eps;
+    const int Nqkv = (s.H + 2 * s.Hkv) * s.Dh;
+    for (int l = 0; l < s.nl; ++l) {
+        const LayerW& w = s.w[l];
+        PrefillLayer& P = s.pf[l];
+        FSB_TRY(launch_rows_of(P.qkv, rows, st));
+        QkvPrepArgs qa{};
+        qa.y = h->ws; qa.ld = Nqkv;
+        qa.bias = w.bqkv;
+        qa.q_norm = s.qk_norm ? w.q_norm : nullptr;
+        qa.k_norm = s.qk_norm ? w.k_norm : nullptr;
+        qa.freqs = s.freqs;
+        qa.row_seq = row_seq;
+        qa.row_pos = row_pos;
+        qa.q = h->q_p;
+        qa.kcache = s.kcache + l * s.cache_layer_stride;
+        qa.vcache = s.vcache + l * s.cache_layer_stride;
+        qa.rows = rows; qa.H = s.H; qa.Hkv = s.Hkv; qa.Dh = s.Dh; qa.S = s.S;
+        qa.eps = eps;
+        FSB_TRY(launch_qkv_prep(qa, st));
+        AttnArgs aa{};
+        aa.q = h->q_p;
+        aa.kcache = qa.kcache;
+        aa.vcache = qa.vcache;
+        aa.row_seq = row_seq;
+        aa.row_pos = row_pos;
+        aa.out = h->attn_p;
+        aa.rows = rows; aa.H = s.H; aa.Hkv = s.Hkv; aa.Dh = s.Dh; aa.S = s.S;
+        aa.window = 0;
+        aa.lcap = h->ctx_lcap;
+        aa.bf16_math = 0;
+        FSB_TRY(launch_attn(aa, st));
+        FSB_TRY(launch_rows_of(P.wo, rows, st));
+        ResidNormArgs r1{};
+        r1.y = h->ws; r1.ld = s.D;
+        r1.bias = w.bo;
+        r1.x_in = h->xres_p; r1.x_out = h->xres_p;
+        r1.norm_w = w.ffn_norm; r1.n_out = h->xn_p;
+        r1.rows = rows; r1.D = s.D; r1.eps = eps;
+        FSB_TRY(launch_resid_norm(r1, st));
+        FSB_TRY(launch_rows_of(P.w13, rows, st));
+        SwigluArgs sa{};
+        sa.y = h->ws; sa.ld = s.n13;
+        sa.h = h->h_p; sa.rows = rows; sa.I = s.I;
+        sa.interleaved = 1;
+        FSB_TRY(launch_swiglu(sa, st));
+        FSB_TRY(launch_rows_of(P.w2, rows, st));
+        ResidNormArgs r2{};
+        r2.y = h->ws; r2.ld = s.D;
+        r2.x_in = h->xres_p; r2.x_out = h->xres_p;
+        // the final norm is applied by the head GEMM's normalise-on-load on the last-token rows only
+        r2.norm_w = (l + 1 < s.nl) ? s.w[l + 1].attn_norm : nullptr;
+        r2.n_out = h->xn_p;
+        r2.rows = rows; r2.D = s.D; r2.eps = eps;
+        FSB_TRY(launch_resid_norm(r2, st));
+    }
+    return 0;
+}
+
+// Head + sampling + fast passes + bookkeeping for `rows` sequences whose last residual-stream rows (un-normed)
+// are in slow.xres[0..rows) with their sums of squares in slow.ssq. inference.py:114-181.
 int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const int* set_pos_rows,
-                   const int* row_pos_src, const fsb_sampling& sp, cudaStream_t st,
-                   DepFlag ready = DepFlag{nullptr, 0}) {
+                   const int* row_pos_src, const fsb_sampling& sp, cudaStream_t st) {
     const fsb_lm_config& c = h->cfg;
     const int C = c.num_codebooks;
     const int* slots = row_slot ? row_slot : h->iota;
-    // ---- slow head over the selectable rows ----
-    DepFlag gd{nullptr, 0};
-    FSB_TRY(launch_dec_gemm(h, h->head_plan, ready, &gd, st));
-    SampleArgs sa{};
-    sa.wait = gd;
-    sa.ctl = slot_ctl(h);
-    sa.parts = parts_of(h->head_plan);
-    sa.n = h->head_rows;
-    sa.rows = rows;
-    sa.temperature = sp.temperature; sa.top_p = sp.top_p; sa.top_k = sp.top_k;
+    Stack& s = h->slow;
+    Stack& f = h->fast;
+    auto launch = [&](const StepGemmPlan& plan) -> int {
+        StepGemmPlan q = plan;
+        q.p.rows = rows;
+        return step_gemm_launch(q, st);
+    };
+    auto sample_args = [&](int n) {
+        SampleArgs a{};
+        a.ctl = slot_ctl(h);
+        a.logits = h->logits_ws;
+        a.ld = h->logits_ld;
+        a.n = n;
+        a.rows = rows;
+        a.temperature = sp.temperature; a.top_p = sp.top_p; a.top_k = sp.top_k;
+        a.seed = sp.seed;
+        a.rng_offset = h->step;
+        a.cur_tok = h->cur_tok;
+        a.num_cb = C;
+        a.row_slot = row_slot;
+        a.noise_u = h->noise_u;
+        a.noise_draws = h->noise_draws;
+        a.noise_ld = h->noise_ld;
+        return a;
+    };
+    // ---- slow head over the selectable rows (final norm applied on load) ----
+    FSB_TRY(launch(h->head_plan));
+    SampleArgs sa = sample_args(h->head_rows);
     sa.slow = 1;
     sa.n_sem = h->head_rows - 1;
     sa.sem_begin = c.semantic_begin_id;
@@ -404,76 +333,49 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
     sa.use_ras = use_ras ? 1 : 0;
     sa.ras_window = h->ras_window;
     sa.ras_update = use_ras ? 1 : 0;
-    sa.seed = sp.seed;
-    sa.rng_offset = h->step;
     sa.draw_id = 0;
-    sa.cur_tok = h->cur_tok;
     sa.cb_index = 0;
-    sa.num_cb = C;
     sa.logits_out = h->slow_logits;
     sa.finished = h->finished;
-    sa.row_slot = row_slot;
     FSB_TRY(launch_sample(sa, st));
 
-    // ---- fast passes ----
-    Stack& f = h->fast;
-    const bf16* hidden = c.norm_fastlayer_input ? h->xn_d : h->xres_d;
-    RowCtx ctx{rows, slots, nullptr, h->xres_d, h->xn_d, h->q_d, h->attn_d, h->h_d, true};
+    // ---- fast pass 0 input: hidden = norm(x) (norm_fastlayer_input) [-> fast_project_in]  (llama.py:459-461, 819-828)
+    RowsArgs hr{};
+    hr.x = s.xres;
+    hr.ssq_in = s.ssq;
+    hr.norm_w = c.norm_fastlayer_input ? h->norm_w : nullptr;
+    hr.rows = rows; hr.D = s.D; hr.eps = c.norm_eps;
+    if (h->has_proj) {
+        hr.y = h->hid_d;
+        FSB_TRY(launch_rows(hr, st));
+        FSB_TRY(launch(h->proj_plan));  // Linear + bias -> fast residual stream (+ its sums of squares)
+    } else {
+        hr.y = f.xres;
+        hr.ssq = f.ssq;
+        FSB_TRY(launch_rows(hr, st));
+    }
     for (int p = 0; p < C; ++p) {
-        ctx.row_pos = h->fpos + p * kDecRows;
-        ResidNormArgs r{};
-        r.rows = rows; r.D = f.D; r.eps = c.norm_eps;
-        r.x_out = h->xres_d;
-        r.norm_w = f.w[0].attn_norm;
-        r.n_out = h->xn_d;
-        if (p == 0) {
-            if (h->has_proj) {
-                // hidden must be the GEMM operand: it already lives in xn_d when norm_fastlayer_input,
-                // otherwise stage it there.
-                if (!c.norm_fastlayer_input)
-                    FSB_CUDA(cudaMemcpyAsync(h->xn_d, h->xres_d, static_cast<size_t>(kDecRows) * h->slow.D * 2,
-                                             cudaMemcpyDeviceToDevice, st));
-                FSB_TRY(gemm_launch(h->proj_plan, st));
-                LinearOutArgs lo{};
-                lo.parts = parts_of(h->proj_plan);
-                lo.bias = h->fast_proj_b;
-                lo.y = h->proj_d; lo.rows = rows; lo.N = f.D;
-                FSB_TRY(launch_linear_out(lo, st));
-                r.x_in = h->proj_d;
-            } else {
-                r.x_in = hidden;
-            }
-            r.done_ctr = flag_new(h);
-            FSB_TRY(launch_resid_norm(r, st));
-        } else {
+        if (p > 0) {
             // input = fast_embeddings[code_{p-1}] ; codes live in cur_tok[slot][p]
-            r.x_in = h->fast_emb;
-            r.gather = h->cur_tok + p;
-            r.gather_map = row_slot;
-            r.done_ctr = flag_new(h);
-            FSB_TRY(launch_resid_norm_g(r, C + 1, st));
+            RowsArgs er{};
+            er.x = h->fast_emb;
+            er.y = f.xres;
+            er.ssq = f.ssq;
+            er.gather = h->cur_tok + p;
+            er.gather_map = row_slot;
+            er.gather_stride = C + 1;
+            er.rows = rows; er.D = f.D; er.eps = c.norm_eps;
+            FSB_TRY(launch_rows(er, st));
         }
-        DepFlag fr{r.done_ctr, static_cast<unsigned>(rows)};
-        FSB_TRY(run_stack(h, f, ctx, h->fast_norm_w, p == 0, nullptr, st, &fr));
+        FSB_TRY(run_stack_decode(h, f, rows, slots, h->fpos + p * kDecRows, p == 0, st));
         if (p == 0) continue;
-        FSB_TRY(launch_dec_gemm(h, h->fast_out_plan, fr, &gd, st));
-        SampleArgs fa{};
-        fa.wait = gd;
-        fa.ctl = slot_ctl(h);
-        fa.parts = parts_of(h->fast_out_plan);
-        fa.n = c.codebook_size;
-        fa.rows = rows;
-        fa.temperature = sp.temperature; fa.top_p = sp.top_p; fa.top_k = sp.top_k;
+        FSB_TRY(launch(h->fast_out_plan));
+        SampleArgs fa = sample_args(c.codebook_size);
         fa.slow = 0;
-        fa.seed = sp.seed;
-        fa.rng_offset = h->step;
         fa.draw_id = p;
-        fa.cur_tok = h->cur_tok;
         fa.cb_index = p;
-        fa.num_cb = C;
         fa.logits_out = h->fast_logits ? h->fast_logits + static_cast<size_t>(p - 1) * c.max_batch * c.codebook_size
                                        : nullptr;
-        fa.row_slot = row_slot;
         FSB_TRY(launch_sample(fa, st));
     }
     FrameEndArgs fe{};
@@ -491,31 +393,27 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
     return 0;
 }
 
-int decode_one_frame(fsb_lm* h, int batch, const fsb_sampling& sp, cudaStream_t st) {
+EmbedArgs embed_args(fsb_lm* h, const int* tokens, bf16* x, float* ssq, int rows) {
     const fsb_lm_config& c = h->cfg;
-    Stack& s = h->slow;
     EmbedArgs ea{};
-    ea.tokens = h->cur_tok;
-    ea.emb = h->emb; ea.cb_emb = h->cb_emb; ea.x = h->xres_d;
-    ea.rows = batch; ea.D = s.D; ea.C = c.num_codebooks; ea.cs = c.codebook_size; ea.vocab = c.vocab_size;
+    ea.tokens = tokens;
+    ea.emb = h->emb; ea.cb_emb = h->cb_emb; ea.x = x; ea.ssq = ssq;
+    ea.rows = rows; ea.D = h->slow.D; ea.C = c.num_codebooks; ea.cs = c.codebook_size; ea.vocab = c.vocab_size;
     ea.sem_begin = c.semantic_begin_id; ea.sem_end = c.semantic_end_id;
     ea.scale = c.scale_codebook_embeddings;
-    FSB_TRY(flags_begin(h, st));
-    FSB_TRY(launch_embed(ea, st));
-    ResidNormArgs r{};
-    r.x_in = h->xres_d;
-    r.norm_w = s.w[0].attn_norm; r.n_out = h->xn_d;
-    r.rows = batch; r.D = s.D; r.eps = c.norm_eps;
-    r.done_ctr = flag_new(h);
-    FSB_TRY(launch_resid_norm(r, st));
-    DepFlag ready{r.done_ctr, static_cast<unsigned>(batch)};
-    bf16* dbg = (h->dbg_x && h->graph_exec == nullptr) ? h->dbg_x : nullptr;
-    if (dbg)
-        FSB_CUDA(cudaMemcpyAsync(dbg, h->xres_d, static_cast<size_t>(batch) * s.D * 2,
-                                 cudaMemcpyDeviceToDevice, st));
-    RowCtx ctx{batch, h->iota, h->pos, h->xres_d, h->xn_d, h->q_d, h->attn_d, h->h_d, true};
-    FSB_TRY(run_stack(h, s, ctx, h->norm_w, false, dbg, st, &ready));
-    return run_frame_tail(h, batch, nullptr, true, nullptr, nullptr, sp, st, ready);
+    return ea;
+}
+
+int decode_one_frame(fsb_lm* h, int batch, const fsb_sampling& sp, cudaStream_t st) {
+    Stack& s = h->slow;
+    FSB_TRY(launch_embed(embed_args(h, h->cur_tok, s.xres, s.ssq, batch), st));
+    FSB_TRY(run_stack_decode(h, s, batch, h->iota, h->pos, false, st));
+    return run_frame_tail(h, batch, nullptr, true, nullptr, nullptr, sp, st);
+}
+
+size_t step_ws_bound(int n_out, int ctas) {
+    const int tiles = cdiv(n_out, 128);
+    return static_cast<size_t>(tiles) * (cdiv(ctas, tiles) + 2) * 128 * 32;
 }
 
 }  // namespace
@@ -525,9 +423,12 @@ extern "C" {
 int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** out) {
     FSB_CHECK(cfg && w && out, "fsb_lm_create: null argument");
     FSB_CHECK(cfg->max_batch >= 1 && cfg->max_batch <= kDecRows, "max_batch must be in [1,32]");
-    FSB_CHECK(cfg->dim % 8 == 0 && cfg->fast_dim % 8 == 0 && cfg->intermediate % 8 == 0 &&
-                  cfg->fast_intermediate % 8 == 0,
-              "dims must be multiples of 8 (TMA 16-byte strides)");
+    FSB_CHECK(cfg->dim % 8 == 0 && cfg->fast_dim % 8 == 0 && cfg->intermediate % 16 == 0 &&
+                  cfg->fast_intermediate % 16 == 0,
+              "dims must be multiples of 8, intermediate sizes of 16 (TMA 16-byte strides, SwiGLU interleave)");
+    FSB_CHECK(cfg->dim <= 4096 && cfg->fast_dim <= 4096, "model dim above 4096 is not supported");
+    FSB_CHECK((cfg->head_dim == 64 || cfg->head_dim == 128) && (cfg->fast_head_dim == 64 || cfg->fast_head_dim == 128),
+              "head_dim must be 64 or 128");
     FSB_CHECK(w->head_rows == cfg->semantic_end_id - cfg->semantic_begin_id + 2, "head_rows mismatch");
     fsb_lm* h = new fsb_lm();
     h->cfg = *cfg;
@@ -538,12 +439,23 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
         delete h;
         return 1;
     }
-    FSB_CHECK(prop.major == 10, "fishb200 kernels are built for sm_100a only (device is sm_%d%d)", prop.major,
-              prop.minor);
-    h->num_sms = prop.multiProcessorCount;
-    if (gemm_init() != 0 || attn_init() != 0) {
+    if (prop.major != 10) {
+        set_error("fishb200 kernels are built for sm_100a only (device is sm_%d%d)", prop.major, prop.minor);
         delete h;
         return 1;
+    }
+    h->num_sms = prop.multiProcessorCount;
+    if (gemm_init() != 0 || attn_init() != 0 || step_gemm_init() != 0) {
+        delete h;
+        return 1;
+    }
+    {
+        // ring depth / CTAs per SM of the step GEMMs are tunable for experiments
+        const char* es = getenv("FSB_STAGES");
+        const char* ec = getenv("FSB_CTAS_PER_SM");
+        h->step_stages = es ? atoi(es) : 5;
+        const int per_sm = ec ? std::max(1, std::min(2, atoi(ec))) : 2;
+        h->step_ctas = h->num_sms * per_sm;
     }
 
     auto B16 = [](const void* p) { return reinterpret_cast<const bf16*>(p); };
@@ -562,11 +474,13 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     Stack& s = h->slow;
     s.D = cfg->dim; s.H = cfg->n_head; s.Hkv = cfg->n_kv_head; s.Dh = cfg->head_dim; s.I = cfg->intermediate;
     s.nl = cfg->n_layer; s.S = cfg->kv_len; s.qk_norm = cfg->qk_norm != 0; s.bf16_math = 0;
+    s.n13 = cdiv(s.I, 64) * 128;
     s.freqs = B16(w->d_freqs);
     Stack& f = h->fast;
     f.D = cfg->fast_dim; f.H = cfg->fast_n_head; f.Hkv = cfg->fast_n_kv_head; f.Dh = cfg->fast_head_dim;
     f.I = cfg->fast_intermediate; f.nl = cfg->n_fast_layer; f.S = cfg->num_codebooks;
     f.qk_norm = cfg->fast_qk_norm != 0; f.bf16_math = 1;
+    f.n13 = cdiv(f.I, 64) * 128;
     f.freqs = B16(w->d_fast_freqs);
     auto copy_layers = [&](Stack& st, const fsb_lm_layer* L) {
         st.w.resize(st.nl);
@@ -582,10 +496,13 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     const int C = cfg->num_codebooks;
     const int Dm = std::max(s.D, f.D), Qm = std::max(s.H * s.Dh, f.H * f.Dh), Im = std::max(s.I, f.I);
     const int Nqkv_s = (s.H + 2 * s.Hkv) * s.Dh, Nqkv_f = (f.H + 2 * f.Hkv) * f.Dh;
-    const int Nmax = std::max({Nqkv_s, Nqkv_f, 2 * s.I, 2 * f.I, s.D, f.D, h->head_rows, cfg->codebook_size});
     const int R = std::max(cfg->max_rows, 128);
-    // partial workspace: decode needs max_parts(<=8) x 32 x N ; prefill needs rows x N
-    h->ws_floats = std::max<size_t>(static_cast<size_t>(24) * kDecRows * Nmax, static_cast<size_t>(R) * Nmax);
+    h->ws_floats = static_cast<size_t>(R) * std::max({Nqkv_s, s.n13, s.D});
+    h->step_ws_floats = 0;
+    for (int n : {Nqkv_s, Nqkv_f, s.n13, f.n13, s.D, f.D, h->head_rows, cfg->codebook_size})
+        h->step_ws_floats = std::max(h->step_ws_floats, step_ws_bound(n, h->step_ctas));
+    h->tile_ctr_len = cdiv(std::max({Nqkv_s, Nqkv_f, s.n13, f.n13, s.D, f.D, h->head_rows, cfg->codebook_size}), 128);
+    h->logits_ld = ((std::max(h->head_rows, cfg->codebook_size) + 3) / 4) * 4;
 #define TRYC(x)                  \
     do {                         \
         if ((x) != 0) {          \
@@ -594,12 +511,17 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
         }                        \
     } while (0)
     TRYC(dalloc(h, &h->ws, h->ws_floats));
-    TRYC(dalloc(h, &h->xres_d, static_cast<size_t>(kDecRows) * Dm));
-    TRYC(dalloc(h, &h->xn_d, static_cast<size_t>(kDecRows) * Dm, "hidden"));
+    TRYC(dalloc(h, &h->step_ws, h->step_ws_floats));
+    TRYC(dalloc(h, &h->tile_ctr, static_cast<size_t>(2 * h->tile_ctr_len)));  // arrivals | completions
+    TRYC(dalloc(h, &s.xres, static_cast<size_t>(kDecRows) * s.D));
+    TRYC(dalloc(h, &s.ssq, static_cast<size_t>(kDecRows) * kSsqStride));
+    TRYC(dalloc(h, &f.xres, static_cast<size_t>(kDecRows) * f.D));
+    TRYC(dalloc(h, &f.ssq, static_cast<size_t>(kDecRows) * kSsqStride));
+    TRYC(dalloc(h, &h->hid_d, static_cast<size_t>(kDecRows) * Dm));
     TRYC(dalloc(h, &h->q_d, static_cast<size_t>(kDecRows) * Qm));
     TRYC(dalloc(h, &h->attn_d, static_cast<size_t>(kDecRows) * Qm));
     TRYC(dalloc(h, &h->h_d, static_cast<size_t>(kDecRows) * Im));
-    TRYC(dalloc(h, &h->proj_d, static_cast<size_t>(kDecRows) * Dm));
+    TRYC(dalloc(h, &h->logits_ws, static_cast<size_t>(kDecRows) * h->logits_ld));
     TRYC(dalloc(h, &h->xres_p, static_cast<size_t>(R) * s.D));
     TRYC(dalloc(h, &h->xn_p, static_cast<size_t>(R) * s.D));
     TRYC(dalloc(h, &h->q_p, static_cast<size_t>(R) * s.H * s.Dh));
@@ -626,15 +548,9 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     TRYC(dalloc(h, &h->iota, kDecRows));
     TRYC(dalloc(h, &h->fpos, static_cast<size_t>(C) * kDecRows));
     TRYC(dalloc(h, &h->step, 1));
-    {
-        const char* ef = getenv("FSB_FLAGS");
-        h->flags_on = ef && ef[0] == '1';
-        if (h->flags_on) TRYC(dalloc(h, &h->flag_base, static_cast<size_t>(fsb_lm::kFlagCap)));
-    }
     if (cfg->debug) {
         TRYC(dalloc(h, &h->slow_logits, static_cast<size_t>(cfg->max_batch) * h->head_rows, "slow_logits"));
         TRYC(dalloc(h, &h->fast_logits, static_cast<size_t>(C) * cfg->max_batch * cfg->codebook_size, "fast_logits"));
-        TRYC(dalloc(h, &h->dbg_x, static_cast<size_t>(s.nl + 1) * kDecRows * s.D, "dbg_x"));
     }
     {
         std::vector<int> io(kDecRows), fp(static_cast<size_t>(C) * kDecRows);
@@ -649,90 +565,57 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
         }
     }
     // ---- GEMM plans ----
+    const float eps = cfg->norm_eps;
     auto build = [&](Stack& st, bool with_prefill) -> int {
         st.dec.resize(st.nl);
         if (with_prefill) st.pf.resize(st.nl);
         const int Nqkv = (st.H + 2 * st.Hkv) * st.Dh;
         for (int l = 0; l < st.nl; ++l) {
             const LayerW& lw = st.w[l];
-            FSB_TRY(make_plan(h, &st.dec[l].qkv, lw.wqkv, Nqkv, st.D, h->xn_d, kDecRows, true));
-            FSB_TRY(make_plan(h, &st.dec[l].wo, lw.wo, st.D, st.H * st.Dh, h->attn_d, kDecRows, true));
-            FSB_TRY(make_plan(h, &st.dec[l].w13, lw.w13, 2 * st.I, st.D, h->xn_d, kDecRows, true));
-            FSB_TRY(make_plan(h, &st.dec[l].w2, lw.w2, st.D, st.I, h->h_d, kDecRows, true));
+            StepLayer& P = st.dec[l];
+            FSB_TRY(make_step_plan(h, &P.qkv, EPI_QKV, lw.wqkv, Nqkv, st.D, nullptr, &st));
+            bind_norm_on_load(&P.qkv, st, lw.attn_norm, eps);
+            P.qkv.p.bias = lw.bqkv;
+            P.qkv.p.q_norm = st.qk_norm ? lw.q_norm : nullptr;
+            P.qkv.p.k_norm = st.qk_norm ? lw.k_norm : nullptr;
+            P.qkv.p.freqs = st.freqs;
+            P.qkv.p.q = h->q_d;
+            P.qkv.p.kcache = st.kcache + l * st.cache_layer_stride;
+            P.qkv.p.vcache = st.vcache + l * st.cache_layer_stride;
+            P.qkv.p.H = st.H; P.qkv.p.Hkv = st.Hkv; P.qkv.p.Dh = st.Dh; P.qkv.p.S = st.S;
+            P.qkv.p.qk_eps = eps;
+            FSB_TRY(make_step_plan(h, &P.wo, EPI_RESID, lw.wo, st.D, st.H * st.Dh, h->attn_d));
+            bind_resid(&P.wo, st, lw.bo, true);
+            FSB_TRY(make_step_plan(h, &P.w13, EPI_SWIGLU, lw.w13, st.n13, st.D, nullptr, &st));
+            bind_norm_on_load(&P.w13, st, lw.ffn_norm, eps);
+            P.w13.p.h = h->h_d;
+            P.w13.p.I = st.I;
+            FSB_TRY(make_step_plan(h, &P.w2, EPI_RESID, lw.w2, st.D, st.I, h->h_d));
+            bind_resid(&P.w2, st, nullptr, true);
             if (with_prefill) {
-                FSB_TRY(make_plan(h, &st.pf[l].qkv, lw.wqkv, Nqkv, st.D, h->xn_p, R, false));
-                FSB_TRY(make_plan(h, &st.pf[l].wo, lw.wo, st.D, st.H * st.Dh, h->attn_p, R, false));
-                FSB_TRY(make_plan(h, &st.pf[l].w13, lw.w13, 2 * st.I, st.D, h->xn_p, R, false));
-                FSB_TRY(make_plan(h, &st.pf[l].w2, lw.w2, st.D, st.I, h->h_p, R, false));
+                FSB_TRY(make_prefill_plan(h, &st.pf[l].qkv, lw.wqkv, Nqkv, st.D, h->xn_p, R));
+                FSB_TRY(make_prefill_plan(h, &st.pf[l].wo, lw.wo, st.D, st.H * st.Dh, h->attn_p, R));
+                FSB_TRY(make_prefill_plan(h, &st.pf[l].w13, lw.w13, st.n13, st.D, h->xn_p, R));
+                FSB_TRY(make_prefill_plan(h, &st.pf[l].w2, lw.w2, st.D, st.I, h->h_p, R));
             }
         }
         return 0;
     };
     TRYC(build(s, true));
     TRYC(build(f, false));
-    {
-        const char* ep = getenv("FSB_PERSISTENT");
-        h->persistent = ep && ep[0] == '1';
-        const char* es = getenv("FSB_PK_STAGES");
-        if (es) h->pk_stages = atoi(es);
+    TRYC(make_step_plan(h, &h->head_plan, EPI_LOGITS, h->head_w, h->head_rows, s.D, nullptr, &s));
+    bind_norm_on_load(&h->head_plan, s, h->norm_w, eps);
+    h->head_plan.p.logits = h->logits_ws;
+    h->head_plan.p.logits_ld = h->logits_ld;
+    TRYC(make_step_plan(h, &h->fast_out_plan, EPI_LOGITS, h->fast_out_w, cfg->codebook_size, f.D, nullptr, &f));
+    bind_norm_on_load(&h->fast_out_plan, f, h->fast_norm_w, eps);
+    h->fast_out_plan.p.logits = h->logits_ws;
+    h->fast_out_plan.p.logits_ld = h->logits_ld;
+    if (h->has_proj) {
+        TRYC(make_step_plan(h, &h->proj_plan, EPI_RESID, h->fast_proj_w, f.D, s.D, h->hid_d));
+        bind_resid(&h->proj_plan, f, h->fast_proj_b, false);
     }
-    {
-        const char* ef = getenv("FSB_FUSED_ATTN");
-        h->fused_prep_attn = ef && (ef[0] == '1' || ef[0] == '2');  // measured slower than qkv_prep + attn (6.45 vs 6.22 ms/frame): off
-        h->fused_fast_only = ef && ef[0] == '2';  // 2: only the fast stack (10-position KV)
-        TRYC(pk_init());
-    }
-    if (h->persistent) {
-        TRYC(dalloc(h, &h->pk_bar, 2));
-        if (getenv("FSB_PK_TRACE")) TRYC(dalloc(h, &h->pk_trace, 1024, "pk_trace"));
-        auto build_pk = [&](Stack& st, const bf16* final_norm) -> int {
-            st.pk.resize(st.nl);
-            std::vector<PkLayer> host(st.nl);
-            const int Nqkv = (st.H + 2 * st.Hkv) * st.Dh;
-            auto fill = [&](PkGemm& g, GemmPlan& p) {
-                g.tmA = p.tmA;
-                g.tmB = p.tmB;
-                g.sched = reinterpret_cast<const int4*>(p.sched_dev);
-                g.cta_items = p.cta_items_dev;
-                g.nparts = p.nparts_dev;
-                g.n_out = p.p.ws_ld;
-                g.max_parts = p.max_parts;
-                g.kblocks = p.p.kb_per_tap;
-                g.slot_stride = p.p.ws_slot_stride;
-            };
-            for (int l = 0; l < st.nl; ++l) {
-                const LayerW& lw = st.w[l];
-                FSB_TRY(make_plan(h, &st.pk[l].qkv, lw.wqkv, Nqkv, st.D, h->xn_d, kDecRows, true, 1));
-                FSB_TRY(make_plan(h, &st.pk[l].wo, lw.wo, st.D, st.H * st.Dh, h->attn_d, kDecRows, true, 1));
-                FSB_TRY(make_plan(h, &st.pk[l].w13, lw.w13, 2 * st.I, st.D, h->xn_d, kDecRows, true, 1));
-                FSB_TRY(make_plan(h, &st.pk[l].w2, lw.w2, st.D, st.I, h->h_d, kDecRows, true, 1));
-                PkLayer& L = host[l];
-                memset(&L, 0, sizeof(L));
-                fill(L.qkv, st.pk[l].qkv);
-                fill(L.wo, st.pk[l].wo);
-                fill(L.w13, st.pk[l].w13);
-                fill(L.w2, st.pk[l].w2);
-                L.bqkv = lw.bqkv;
-                L.q_norm = st.qk_norm ? lw.q_norm : nullptr;
-                L.k_norm = st.qk_norm ? lw.k_norm : nullptr;
-                L.bo = lw.bo;
-                L.ffn_norm = lw.ffn_norm;
-                L.next_norm = (l + 1 < st.nl) ? st.w[l + 1].attn_norm : final_norm;
-                L.kcache = st.kcache + l * st.cache_layer_stride;
-                L.vcache = st.vcache + l * st.cache_layer_stride;
-            }
-            FSB_TRY(dalloc(h, &st.pk_layers, static_cast<size_t>(st.nl)));
-            FSB_CUDA(cudaMemcpy(st.pk_layers, host.data(), host.size() * sizeof(PkLayer), cudaMemcpyHostToDevice));
-            return 0;
-        };
-        TRYC(build_pk(s, h->norm_w));
-        TRYC(build_pk(f, h->fast_norm_w));
-    }
-    TRYC(make_plan(h, &h->head_plan, h->head_w, h->head_rows, s.D, h->xn_d, kDecRows, true));
-    TRYC(make_plan(h, &h->fast_out_plan, h->fast_out_w, cfg->codebook_size, f.D, h->xn_d, kDecRows, true));
-    if (h->has_proj) TRYC(make_plan(h, &h->proj_plan, h->fast_proj_w, f.D, s.D, h->xn_d, kDecRows, true));
 #undef TRYC
-    h->named["ws"] = {h->ws, h->ws_floats * 4};
     *out = h;
     return 0;
 }
@@ -741,15 +624,14 @@ void fsb_lm_destroy(fsb_lm* h) {
     if (!h) return;
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     auto free_plans = [](Stack& st) {
-        for (auto& p : st.dec) { gemm_plan_free(&p.qkv); gemm_plan_free(&p.wo); gemm_plan_free(&p.w13); gemm_plan_free(&p.w2); }
+        for (auto& p : st.dec) { step_plan_free(&p.qkv); step_plan_free(&p.wo); step_plan_free(&p.w13); step_plan_free(&p.w2); }
         for (auto& p : st.pf) { gemm_plan_free(&p.qkv); gemm_plan_free(&p.wo); gemm_plan_free(&p.w13); gemm_plan_free(&p.w2); }
-        for (auto& p : st.pk) { gemm_plan_free(&p.qkv); gemm_plan_free(&p.wo); gemm_plan_free(&p.w13); gemm_plan_free(&p.w2); }
     };
     free_plans(h->slow);
     free_plans(h->fast);
-    gemm_plan_free(&h->head_plan);
-    gemm_plan_free(&h->fast_out_plan);
-    if (h->has_proj) gemm_plan_free(&h->proj_plan);
+    step_plan_free(&h->head_plan);
+    step_plan_free(&h->fast_out_plan);
+    if (h->has_proj) step_plan_free(&h->proj_plan);
     for (void* p : h->owned) cudaFree(p);
     delete h;
 }
@@ -774,35 +656,44 @@ int fsb_lm_prefill(fsb_lm* h, const int32_t* d_tokens, const int32_t* d_row_slot
     FSB_CHECK(rows >= 1 && rows <= std::max(c.max_rows, 128), "prefill: rows=%d exceeds max_rows=%d", rows, c.max_rows);
     FSB_CHECK(nseq >= 1 && nseq <= c.max_batch, "prefill: nseq=%d out of range", nseq);
     Stack& s = h->slow;
-    EmbedArgs ea{};
-    ea.tokens = d_tokens;
-    ea.emb = h->emb; ea.cb_emb = h->cb_emb; ea.x = h->xres_p;
-    ea.rows = rows; ea.D = s.D; ea.C = c.num_codebooks; ea.cs = c.codebook_size; ea.vocab = c.vocab_size;
-    ea.sem_begin = c.semantic_begin_id; ea.sem_end = c.semantic_end_id;
-    ea.scale = c.scale_codebook_embeddings;
-    FSB_TRY(launch_embed(ea, st));
+    FSB_TRY(launch_embed(embed_args(h, d_tokens, h->xres_p, nullptr, rows), st));
     ResidNormArgs r{};
     r.x_in = h->xres_p;
     r.norm_w = s.w[0].attn_norm; r.n_out = h->xn_p;
     r.rows = rows; r.D = s.D; r.eps = c.norm_eps;
     FSB_TRY(launch_resid_norm(r, st));
-    RowCtx ctx{rows, d_row_slot, d_row_pos, h->xres_p, h->xn_p, h->q_p, h->attn_p, h->h_p, false};
-    FSB_TRY(run_stack(h, s, ctx, h->norm_w, false, nullptr, st));
+    FSB_TRY(run_stack_prefill(h, s, rows, d_row_slot, d_row_pos, st));
     if (!do_sample) return 0;
     FSB_CHECK(sp != nullptr || h->slot_control, "prefill: sampling parameters required");
     const fsb_sampling sp_none{1.f, 1.f, 1, 0};
     if (sp == nullptr) sp = &sp_none;
-    // last-token rows -> decode workspaces (llama.py:447-448 keeps only the last position)
-    FSB_TRY(launch_gather_rows(h->xn_p, d_last_rows, h->xn_d, nseq, s.D, st));
-    FSB_TRY(launch_gather_rows(h->xres_p, d_last_rows, h->xres_d, nseq, s.D, st));
+    // last-token rows -> decode residual stream (llama.py:447-448 keeps only the last position)
+    RowsArgs g{};
+    g.x = h->xres_p;
+    g.y = s.xres;
+    g.ssq = s.ssq;
+    g.gather = d_last_rows;
+    g.gather_stride = 1;
+    g.rows = nseq; g.D = s.D; g.eps = c.norm_eps;
+    FSB_TRY(launch_rows(g, st));
     // the reference resets the RAS window per generate() call and prefill uses no RAS
-    FSB_TRY(flags_begin(h, st));
     return run_frame_tail(h, nseq, d_slots, false, d_last_rows, d_row_pos, *sp, st);
 }
 
 int fsb_lm_set_slot_control(fsb_lm* h, int enable) {
     FSB_CHECK(h != nullptr, "set_slot_control: null handle");
     h->slot_control = enable != 0;
+    return 0;
+}
+
+int fsb_lm_set_sampler_noise(fsb_lm* h, const float* d_u, int draws_per_frame, int ld) {
+    FSB_CHECK(h != nullptr, "set_sampler_noise: null handle");
+    FSB_CHECK(d_u == nullptr || (draws_per_frame >= 2 * h->cfg.num_codebooks && ld >= h->head_rows && ld >= h->cfg.codebook_size),
+              "set_sampler_noise: need >= %d draws per frame and ld >= %d", 2 * h->cfg.num_codebooks,
+              std::max(h->head_rows, h->cfg.codebook_size));
+    h->noise_u = d_u;
+    h->noise_draws = draws_per_frame;
+    h->noise_ld = ld;
     return 0;
 }
 
@@ -813,16 +704,11 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int
     const fsb_sampling sp_none{1.f, 1.f, 1, 0};
     if (sp == nullptr || h->slot_control) sp = &sp_none;  // per-slot parameters: one graph for every mix of requests
     if (!use_graph) {
-        if (h->graph_exec) {  // debug copies are only recorded outside graphs
-            cudaGraphExecDestroy(h->graph_exec);
-            h->graph_exec = nullptr;
-            h->graph_batch = -1;
-        }
         for (int i = 0; i < nframes; ++i) FSB_TRY(decode_one_frame(h, batch, *sp, st));
         return 0;
     }
     const bool same = h->graph_exec && h->graph_batch == batch && h->graph_lcap == h->ctx_lcap &&
-                      h->graph_slot_control == h->slot_control &&
+                      h->graph_slot_control == h->slot_control && h->graph_noise == h->noise_u &&
                       memcmp(&h->graph_sampling, sp, sizeof(fsb_sampling)) == 0;
     if (!same) {
         if (h->graph_exec) {
@@ -833,8 +719,6 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int
         cudaStream_t cs;
         FSB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         cudaGraph_t g = nullptr;
-        cudaGraphExec_t sentinel = reinterpret_cast<cudaGraphExec_t>(1);
-        h->graph_exec = sentinel;  // suppress debug copies while capturing
         cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
         int rc = 1;
         const int launches_before = g_launch_count;
@@ -844,7 +728,6 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int
         }
         h->graph_kernels = g_launch_count - launches_before;
         g_launch_count = launches_before;  // captured, not launched
-        h->graph_exec = nullptr;
         if (e != cudaSuccess || rc != 0 || g == nullptr) {
             if (rc == 0) set_error("decode: graph capture failed: %s", cudaGetErrorString(e));
             cudaStreamDestroy(cs);
@@ -863,6 +746,7 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int
         h->graph_batch = batch;
         h->graph_lcap = h->ctx_lcap;
         h->graph_slot_control = h->slot_control;
+        h->graph_noise = h->noise_u;
         h->graph_sampling = *sp;
     }
     for (int i = 0; i < nframes; ++i) {
@@ -872,59 +756,43 @@ int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* sp, int
     return 0;
 }
 
-int fsb_lm_trace_gemms(fsb_lm* h, unsigned long long* d_trace, int max_launches, int* grid_out, void* stream) {
-    // One slow layer's four GEMMs repeated, each CTA recording globaltimer at start / after the
-    // programmatic-dependency wait / at exit: shows whether consecutive kernels really overlap.
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    Stack& s = h->slow;
-    int id = 0;
-    for (int l = 0; l < s.nl && id + 4 <= max_launches; ++l) {
-        GemmPlan* plans[4] = {&s.dec[l].qkv, &s.dec[l].wo, &s.dec[l].w13, &s.dec[l].w2};
-        for (int k = 0; k < 4; ++k) {
-            GemmPlan q = *plans[k];
-            q.p.trace = d_trace;
-            q.p.trace_id = id++;
-            FSB_TRY(gemm_launch(q, st));
-        }
-    }
-    if (grid_out) *grid_out = static_cast<int>(s.dec[0].qkv.grid.x);
-    return id;
-}
-
 int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* launches_per_rep, void* stream) {
-    // Every weight-streaming GEMM of one decode frame (36 slow layers x 4, head, 10 fast passes x
-    // (4 layers x 4 + head)) back to back, without the glue kernels: the measured stream of the
-    // dominant kernel for the roofline line of bench.py. Operands are whatever the workspaces hold.
+    // Every weight-streaming step GEMM of one decode frame (36 slow layers x 4, head, 10 fast passes x
+    // (4 layers x 4 + head)) back to back, without the attention / sampling kernels: the measured stream of the
+    // dominant kernel for the roofline line of bench.py. Operands are whatever the workspaces hold; the
+    // epilogues run (and overwrite the decode state), so call it after the timed generation only.
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const fsb_lm_config& c = h->cfg;
     double bytes = 0;
     int launches = 0;
-    auto run = [&](const GemmPlan& p, double wbytes) -> int {
-        bytes += wbytes;
+    const int rows = c.max_batch;
+    auto run = [&](const StepGemmPlan& p, const int* row_pos) -> int {
+        bytes += p.weight_bytes;
         ++launches;
-        return gemm_launch(p, st);
+        StepGemmPlan q = p;
+        q.p.rows = rows;
+        q.p.row_seq = h->iota;
+        q.p.row_pos = row_pos;
+        return step_gemm_launch(q, st);
     };
     for (int r = 0; r < reps; ++r) {
         bytes = 0;
         launches = 0;
-        auto stack = [&](Stack& s, bool skip_tail) -> int {
-            const double nq = static_cast<double>((s.H + 2 * s.Hkv) * s.Dh) * s.D * 2;
-            const double no = static_cast<double>(s.D) * s.H * s.Dh * 2;
-            const double n13 = 2.0 * s.I * s.D * 2, n2 = static_cast<double>(s.D) * s.I * 2;
+        auto stack = [&](Stack& s, bool skip_tail, const int* row_pos) -> int {
             for (int l = 0; l < s.nl; ++l) {
-                FSB_TRY(run(s.dec[l].qkv, nq));
+                FSB_TRY(run(s.dec[l].qkv, row_pos));
                 if (skip_tail && l == s.nl - 1) break;
-                FSB_TRY(run(s.dec[l].wo, no));
-                FSB_TRY(run(s.dec[l].w13, n13));
-                FSB_TRY(run(s.dec[l].w2, n2));
+                FSB_TRY(run(s.dec[l].wo, row_pos));
+                FSB_TRY(run(s.dec[l].w13, row_pos));
+                FSB_TRY(run(s.dec[l].w2, row_pos));
             }
             return 0;
         };
-        FSB_TRY(stack(h->slow, false));
-        FSB_TRY(run(h->head_plan, static_cast<double>(h->head_rows) * c.dim * 2));
+        FSB_TRY(stack(h->slow, false, h->pos));
+        FSB_TRY(run(h->head_plan, h->pos));
         for (int p = 0; p < c.num_codebooks; ++p) {
-            FSB_TRY(stack(h->fast, p == 0));
-            if (p > 0) FSB_TRY(run(h->fast_out_plan, static_cast<double>(c.codebook_size) * c.fast_dim * 2));
+            FSB_TRY(stack(h->fast, p == 0, h->fpos + p * kDecRows));
+            if (p > 0) FSB_TRY(run(h->fast_out_plan, h->fpos));
         }
     }
     if (weight_bytes_per_rep) *weight_bytes_per_rep = bytes;

@@ -1,83 +1,150 @@
-// See lm_kernels.cuh.  All kernels here are HBM/L2-bound glue between the GEMMs: vectorised,
-// coalesced, warp-shuffle reductions, fp32 math with bf16 rounding at the reference's rounding points.
+// See lm_kernels.cuh.  All kernels here are HBM/L2-bound glue: vectorised, coalesced, warp-shuffle
+// reductions, fp32 math with bf16 rounding at the reference's rounding points.
 #include "lm_kernels.cuh"
+
+#include "lm_gemm.cuh"
 
 namespace fsb {
 
 namespace {
 
+// Sum of squares of 4 consecutive features per lane over one 128-feature tile -> all lanes.
+__device__ __forceinline__ float tile_ssq(const float (&x)[4]) {
+    return warp_sum(((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2]) + x[3] * x[3]);
+}
+
 // ------------------------------------------------------------------------------------------------
-// embed: llama.py:399-420
+// embed: llama.py:399-420 (+ per-tile sum of squares for the first layer's normalise-on-load)
 // ------------------------------------------------------------------------------------------------
-__global__ void embed_kernel(EmbedArgs a, float inv_div) {
+constexpr int kRowThreads = 256;
+
+__global__ void __launch_bounds__(kRowThreads) embed_kernel(EmbedArgs a, float inv_div) {
     pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int* t = a.tokens + static_cast<size_t>(row) * (a.C + 1);
     int tok = t[0];
     const bool sem = tok >= a.sem_begin && tok <= a.sem_end;
     tok = min(max(tok, 0), a.vocab - 1);
-    for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
-        float s = 0.f;
-        if (sem) {
-            for (int c = 0; c < a.C; ++c) {
-                int code = min(max(t[c + 1], 0), a.cs - 1);
-                s += bf2f(a.cb_emb[(static_cast<size_t>(c) * a.cs + code) * a.D + d]);
+    const int nt = (a.D + kSsqTile - 1) / kSsqTile;
+    for (int tile = warp; tile < nt; tile += kRowThreads / 32) {
+        const int f = tile * kSsqTile + lane * 4;
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        if (f < a.D) {  // D % 4 == 0
+            float s[4] = {0.f, 0.f, 0.f, 0.f};
+            if (sem) {
+                for (int c = 0; c < a.C; ++c) {
+                    const int code = min(max(t[c + 1], 0), a.cs - 1);
+                    const uint2 u = *reinterpret_cast<const uint2*>(a.cb_emb + (static_cast<size_t>(c) * a.cs + code) * a.D + f);
+                    s[0] += bf_lo(u.x); s[1] += bf_hi(u.x); s[2] += bf_lo(u.y); s[3] += bf_hi(u.y);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s[q] = rbf(s[q]);  // torch.stack(...).sum(dim=1) -> one bf16 rounding
             }
-            s = rbf(s);  // torch.stack(...).sum(dim=1) -> one bf16 rounding
+            const uint2 e = *reinterpret_cast<const uint2*>(a.emb + static_cast<size_t>(tok) * a.D + f);
+            const float ev[4] = {bf_lo(e.x), bf_hi(e.x), bf_lo(e.y), bf_hi(e.y)};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                x[q] = rbf(ev[q] + s[q]);
+                if (sem && a.scale) x[q] = rbf(x[q] / inv_div);  // x / sqrt(C+1)
+            }
+            uint2 o;
+            o.x = pack_bf2(x[0], x[1]);
+            o.y = pack_bf2(x[2], x[3]);
+            *reinterpret_cast<uint2*>(a.x + static_cast<size_t>(row) * a.D + f) = o;
         }
-        float x = rbf(bf2f(a.emb[static_cast<size_t>(tok) * a.D + d]) + s);
-        if (sem && a.scale) x = rbf(x / inv_div);  // x / sqrt(C+1)
-        a.x[static_cast<size_t>(row) * a.D + d] = f2bf(x);
+        const float ss = tile_ssq(x);
+        if (a.ssq != nullptr && lane == 0) a.ssq[row * kSsqRowStride + tile] = ss;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// residual add + fish RMSNorm
+// rows: gather (+ fish RMSNorm) of whole rows into a residual stream, with its per-tile sum of squares
+// ------------------------------------------------------------------------------------------------
+constexpr int kRowsMaxTilesPerWarp = 4;  // D <= 4096 with 8 warps
+
+__global__ void __launch_bounds__(kRowThreads) rows_kernel(RowsArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = a.gather_map ? a.gather_map[row] : row;
+    const int src = a.gather ? a.gather[static_cast<size_t>(m) * a.gather_stride] : row;
+    const int nt = (a.D + kSsqTile - 1) / kSsqTile;
+    float x[kRowsMaxTilesPerWarp][4];
+#pragma unroll
+    for (int e = 0; e < kRowsMaxTilesPerWarp; ++e) {
+        const int tile = warp + e * (kRowThreads / 32);
+        const int f = tile * kSsqTile + lane * 4;
+        x[e][0] = x[e][1] = x[e][2] = x[e][3] = 0.f;
+        if (tile < nt && f < a.D) {
+            const uint2 u = *reinterpret_cast<const uint2*>(a.x + static_cast<size_t>(src) * a.D + f);
+            x[e][0] = bf_lo(u.x); x[e][1] = bf_hi(u.x); x[e][2] = bf_lo(u.y); x[e][3] = bf_hi(u.y);
+        }
+    }
+    float r = 1.f;
+    if (a.norm_w != nullptr) {
+        // the row's sum of squares as the producing kernel left it, added tile by tile in tile order: exactly
+        // what the step GEMM's normalise-on-load computes, so both see the same rsqrt
+        const float* q = a.ssq_in + static_cast<size_t>(src) * kSsqRowStride;
+        float tot = 0.f;
+        for (int t = 0; t < nt; ++t) tot += q[t];
+        r = rsqrtf(tot / static_cast<float>(a.D) + a.eps);
+    }
+#pragma unroll
+    for (int e = 0; e < kRowsMaxTilesPerWarp; ++e) {
+        const int tile = warp + e * (kRowThreads / 32);
+        const int f = tile * kSsqTile + lane * 4;
+        const bool live = tile < nt && f < a.D;
+        if (live && a.norm_w != nullptr) {
+            const uint2 w = *reinterpret_cast<const uint2*>(a.norm_w + f);
+            const float wf[4] = {bf_lo(w.x), bf_hi(w.x), bf_lo(w.y), bf_hi(w.y)};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[e][q] = rbf(rbf(x[e][q] * r) * wf[q]);
+        }
+        if (live) {
+            uint2 o;
+            o.x = pack_bf2(x[e][0], x[e][1]);
+            o.y = pack_bf2(x[e][2], x[e][3]);
+            *reinterpret_cast<uint2*>(a.y + static_cast<size_t>(row) * a.D + f) = o;
+        }
+        if (tile < nt) {
+            const float ss = tile_ssq(x[e]);
+            if (a.ssq != nullptr && lane == 0) a.ssq[row * kSsqRowStride + tile] = ss;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual add + fish RMSNorm on a plain fp32 GEMM result (prefill, codec transformer)
 // ------------------------------------------------------------------------------------------------
 constexpr int kRnThreads = 512;
 constexpr int kRnMaxPer = 8;  // D <= 4096
 
-// kFlags = device-side dependency flags (opt-in experiment). The default instantiation keeps exactly the
-// grid-dependency code: the flag plumbing changed the register allocation of this kernel (128 -> 99, fewer
-// partial-sum loads in flight) and cost 0.7 ms per frame even when unused.
-template <bool kFlags>
-__global__ void __launch_bounds__(kRnThreads) resid_norm_kernel(ResidNormCore a, int gstride, DepFlag wait,
-                                                                unsigned* done_ctr) {
+__global__ void __launch_bounds__(kRnThreads) resid_norm_kernel(ResidNormArgs a) {
     pdl_launch_dependents();
-    if constexpr (kFlags) dep_wait_cta(wait);
-    else pdl_wait();
+    pdl_wait();
     __shared__ float red[33];
     const int row = blockIdx.x;
-    const int grow = a.gather_map ? a.gather_map[row] : row;
-    const int src = a.gather ? a.gather[static_cast<size_t>(grow) * gstride] : row;
-    float v[kRnMaxPer], y[kRnMaxPer];
-    int rws[kRnMaxPer], fts[kRnMaxPer];
-    bool ok[kRnMaxPer];
-#pragma unroll
-    for (int e = 0; e < kRnMaxPer; ++e) {
-        fts[e] = threadIdx.x + e * kRnThreads;
-        rws[e] = row;
-        ok[e] = fts[e] < a.D;
-        v[e] = (ok[e] && a.x_in) ? bf2f(a.x_in[static_cast<size_t>(src) * a.D + fts[e]]) : 0.f;
-        y[e] = 0.f;
-    }
-    if (a.parts.ws) sum_parts_n<kRnMaxPer>(a.parts, rws, fts, ok, y, a.parts.max_parts > 0 ? a.parts.max_parts : 1);
+    float v[kRnMaxPer];
     float ss = 0.f;
 #pragma unroll
     for (int e = 0; e < kRnMaxPer; ++e) {
-        if (ok[e]) {
-            float x = v[e];
-            if (a.parts.ws) {
-                float yy = y[e];
-                if (a.bias) yy += bf2f(a.bias[fts[e]]);
+        const int f = threadIdx.x + e * kRnThreads;
+        v[e] = 0.f;
+        if (f < a.D) {
+            float x = a.x_in ? bf2f(a.x_in[static_cast<size_t>(row) * a.D + f]) : 0.f;
+            if (a.y) {
+                float yy = a.y[static_cast<size_t>(row) * a.ld + f];
+                if (a.bias) yy += bf2f(a.bias[f]);
                 yy = rbf(yy);
-                if (a.scale) yy *= bf2f(a.scale[fts[e]]);
+                if (a.scale) yy *= bf2f(a.scale[f]);
                 x = rbf(x + yy);
             }
             v[e] = x;
             ss += x * x;
-            if (a.x_out) a.x_out[static_cast<size_t>(row) * a.D + fts[e]] = f2bf(x);
+            if (a.x_out) a.x_out[static_cast<size_t>(row) * a.D + f] = f2bf(x);
         }
     }
     if (a.norm_w != nullptr) {
@@ -85,92 +152,43 @@ __global__ void __launch_bounds__(kRnThreads) resid_norm_kernel(ResidNormCore a,
         const float r = rsqrtf(tot / static_cast<float>(a.D) + a.eps);
 #pragma unroll
         for (int e = 0; e < kRnMaxPer; ++e) {
-            if (ok[e]) {
-                const float n = rbf(rbf(v[e] * r) * bf2f(a.norm_w[fts[e]]));
-                a.n_out[static_cast<size_t>(row) * a.D + fts[e]] = f2bf(n);
-            }
+            const int f = threadIdx.x + e * kRnThreads;
+            if (f < a.D) a.n_out[static_cast<size_t>(row) * a.D + f] = f2bf(rbf(rbf(v[e] * r) * bf2f(a.norm_w[f])));
         }
     }
-    if constexpr (kFlags) dep_signal_cta(done_ctr);
 }
 
-// Vectorised form (D % 4 == 0): a thread owns groups of 4 consecutive features, so one 16-byte load fetches a
-// slot's partials for all four and the slot loop issues 4x fewer instructions (the scalar kernel executes ~1400
-// instructions per warp for 80 useful loads and is issue/latency bound at 16 warps per SM, ncu). The per-feature
-// additions are in the same slot order as sum_parts(): identical partial sums.
-constexpr int kRn4MaxThreads = 640;
-template <bool kFlags, int GP, int U>
-__global__ void __launch_bounds__(kRn4MaxThreads) resid_norm4_kernel(ResidNormCore a, int gstride, DepFlag wait,
-                                                                      unsigned* done_ctr) {
+// Vectorised form (D % 4 == 0, ld % 4 == 0): 4 consecutive features per thread, 16-byte loads of y.
+constexpr int kRn4Threads = 256;
+constexpr int kRn4MaxPer = 4;  // D <= 4096
+__global__ void __launch_bounds__(kRn4Threads) resid_norm4_kernel(ResidNormArgs a) {
     pdl_launch_dependents();
-    if constexpr (kFlags) dep_wait_cta(wait);
-    else pdl_wait();
+    pdl_wait();
     __shared__ float red[33];
     const int row = blockIdx.x;
-    const int grow = a.gather_map ? a.gather_map[row] : row;
-    const int src = a.gather ? a.gather[static_cast<size_t>(grow) * gstride] : row;
-    const int G = a.D >> 2;
-    int f[GP];
-    bool ok[GP];
-    float4 y[GP];
-#pragma unroll
-    for (int e = 0; e < GP; ++e) {
-        const int g = threadIdx.x + e * blockDim.x;
-        ok[e] = g < G;
-        f[e] = ok[e] ? g * 4 : 0;
-        y[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (a.parts.ws) {
-        int np[GP];
-        const float4* p[GP];
-        const size_t ss4 = static_cast<size_t>(a.parts.slot_stride) >> 2;
-        const int maxp = a.parts.max_parts > 0 ? a.parts.max_parts : 1;
-#pragma unroll
-        for (int e = 0; e < GP; ++e) {
-            np[e] = ok[e] ? (a.parts.nparts ? __ldg(a.parts.nparts + (f[e] >> 7)) : 1) : 0;
-            p[e] = reinterpret_cast<const float4*>(a.parts.ws + static_cast<size_t>(row) * a.parts.ld + f[e]);
-        }
-        for (int q = 0; q < maxp; q += U) {
-            float4 t[GP][U];
-#pragma unroll
-            for (int e = 0; e < GP; ++e)
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    t[e][u] = (q + u < np[e]) ? p[e][static_cast<size_t>(q + u) * ss4] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int e = 0; e < GP; ++e) {
-                if (q < np[e]) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        y[e].x += t[e][u].x;
-                        y[e].y += t[e][u].y;
-                        y[e].z += t[e][u].z;
-                        y[e].w += t[e][u].w;
-                    }
-                }
-            }
-        }
-    }
-    float v[GP][4];
+    float v[kRn4MaxPer][4];
     float ss = 0.f;
 #pragma unroll
-    for (int e = 0; e < GP; ++e) {
-        if (!ok[e]) continue;
+    for (int e = 0; e < kRn4MaxPer; ++e) {
+        const int f = (threadIdx.x + e * kRn4Threads) * 4;
+        v[e][0] = v[e][1] = v[e][2] = v[e][3] = 0.f;
+        if (f >= a.D) continue;
         float x[4] = {0.f, 0.f, 0.f, 0.f};
         if (a.x_in) {
-            const uint2 u = *reinterpret_cast<const uint2*>(a.x_in + static_cast<size_t>(src) * a.D + f[e]);
+            const uint2 u = *reinterpret_cast<const uint2*>(a.x_in + static_cast<size_t>(row) * a.D + f);
             x[0] = bf_lo(u.x); x[1] = bf_hi(u.x); x[2] = bf_lo(u.y); x[3] = bf_hi(u.y);
         }
-        if (a.parts.ws) {
-            float yy[4] = {y[e].x, y[e].y, y[e].z, y[e].w};
+        if (a.y) {
+            const float4 y4 = *reinterpret_cast<const float4*>(a.y + static_cast<size_t>(row) * a.ld + f);
+            float yy[4] = {y4.x, y4.y, y4.z, y4.w};
             if (a.bias) {
-                const uint2 b = *reinterpret_cast<const uint2*>(a.bias + f[e]);
+                const uint2 b = *reinterpret_cast<const uint2*>(a.bias + f);
                 yy[0] += bf_lo(b.x); yy[1] += bf_hi(b.x); yy[2] += bf_lo(b.y); yy[3] += bf_hi(b.y);
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) yy[c] = rbf(yy[c]);
             if (a.scale) {
-                const uint2 sc = *reinterpret_cast<const uint2*>(a.scale + f[e]);
+                const uint2 sc = *reinterpret_cast<const uint2*>(a.scale + f);
                 yy[0] *= bf_lo(sc.x); yy[1] *= bf_hi(sc.x); yy[2] *= bf_lo(sc.y); yy[3] *= bf_hi(sc.y);
             }
 #pragma unroll
@@ -185,16 +203,17 @@ __global__ void __launch_bounds__(kRn4MaxThreads) resid_norm4_kernel(ResidNormCo
             uint2 o;
             o.x = pack_bf2(x[0], x[1]);
             o.y = pack_bf2(x[2], x[3]);
-            *reinterpret_cast<uint2*>(a.x_out + static_cast<size_t>(row) * a.D + f[e]) = o;
+            *reinterpret_cast<uint2*>(a.x_out + static_cast<size_t>(row) * a.D + f) = o;
         }
     }
     if (a.norm_w != nullptr) {
         const float tot = block_sum(ss, red);
         const float r = rsqrtf(tot / static_cast<float>(a.D) + a.eps);
 #pragma unroll
-        for (int e = 0; e < GP; ++e) {
-            if (!ok[e]) continue;
-            const uint2 w = *reinterpret_cast<const uint2*>(a.norm_w + f[e]);
+        for (int e = 0; e < kRn4MaxPer; ++e) {
+            const int f = (threadIdx.x + e * kRn4Threads) * 4;
+            if (f >= a.D) continue;
+            const uint2 w = *reinterpret_cast<const uint2*>(a.norm_w + f);
             const float wf[4] = {bf_lo(w.x), bf_hi(w.x), bf_lo(w.y), bf_hi(w.y)};
             float n[4];
 #pragma unroll
@@ -202,46 +221,25 @@ __global__ void __launch_bounds__(kRn4MaxThreads) resid_norm4_kernel(ResidNormCo
             uint2 o;
             o.x = pack_bf2(n[0], n[1]);
             o.y = pack_bf2(n[2], n[3]);
-            *reinterpret_cast<uint2*>(a.n_out + static_cast<size_t>(row) * a.D + f[e]) = o;
+            *reinterpret_cast<uint2*>(a.n_out + static_cast<size_t>(row) * a.D + f) = o;
         }
     }
-    if constexpr (kFlags) dep_signal_cta(done_ctr);
-}
-
-__global__ void linear_out_kernel(LinearOutArgs a) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int row = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.N) return;
-    float y = sum_parts(a.parts, row, i);
-    if (a.bias) y += bf2f(a.bias[i]);
-    a.y[static_cast<size_t>(row) * a.N + i] = f2bf(y);
 }
 
 // ------------------------------------------------------------------------------------------------
 // q/k/v post-processing: llama.py:891-911
 // ------------------------------------------------------------------------------------------------
-template <bool kFlags>
-__global__ void qkv_prep_kernel(QkvPrepCore a, DepFlag wait) {
+__global__ void qkv_prep_kernel(QkvPrepArgs a) {
     pdl_launch_dependents();
-    if constexpr (kFlags) dep_wait_cta(wait);
-    else pdl_wait();
+    pdl_wait();
     __shared__ float red[33];
     const int row = blockIdx.x, head = blockIdx.y;
     const int t = threadIdx.x;  // pair index, Dh/2 threads
     const int Dh = a.Dh;
     const int kind = head < a.H ? 0 : (head < a.H + a.Hkv ? 1 : 2);  // q, k, v
     const int f0 = head * Dh + 2 * t;
-    float v0, v1;
-    {
-        const int rws[2] = {row, row}, fts[2] = {f0, f0 + 1};
-        const bool ok[2] = {true, true};
-        float y[2];
-        sum_parts_n<2>(a.parts, rws, fts, ok, y, a.parts.max_parts > 0 ? a.parts.max_parts : 1);
-        v0 = y[0];
-        v1 = y[1];
-    }
+    const float2 y2 = *reinterpret_cast<const float2*>(a.y + static_cast<size_t>(row) * a.ld + f0);
+    float v0 = y2.x, v1 = y2.y;
     if (a.bias) {
         v0 += bf2f(a.bias[f0]);
         v1 += bf2f(a.bias[f0 + 1]);
@@ -269,7 +267,7 @@ __global__ void qkv_prep_kernel(QkvPrepCore a, DepFlag wait) {
     if (kind == 0) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(a.q + (static_cast<size_t>(row) * a.H + head) * Dh);
         dst[t] = packed;
-    } else {
+    } else if (pos < a.S) {
         const int g = kind == 1 ? head - a.H : head - a.H - a.Hkv;
         __nv_bfloat16* cache = kind == 1 ? a.kcache : a.vcache;
         const int b = a.row_seq[row];
@@ -285,8 +283,8 @@ __global__ void qkv_prep_kernel(QkvPrepCore a, DepFlag wait) {
 constexpr int kAttnThreads = 256;
 constexpr int kAttnWarps = kAttnThreads / 32;
 
-template <int DH, int G, bool kFlags>
-__global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnCore a, float scale, int lcap, unsigned* done_ctr) {
+template <int DH, int G>
+__global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnArgs a, float scale, int lcap) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ float sm[];
@@ -296,7 +294,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnCore a, float sc
     __shared__ float red2[33];
     const int row = blockIdx.y, g = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = a.row_seq[row], pos = a.row_pos[row];
+    const int b = a.row_seq[row], pos = min(a.row_pos[row], a.S - 1);  // a position past the cache reads its last row
     const int lo = (a.window > 0 && pos - a.window + 1 > 0) ? pos - a.window + 1 : 0;
     const int L = pos - lo + 1;
     const size_t cache_base = ((static_cast<size_t>(b) * a.Hkv + g) * a.S + lo) * DH;
@@ -416,75 +414,49 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnCore a, float sc
         const int gg = e / DH, d = e - gg * DH;
         a.out[(static_cast<size_t>(row) * a.H + g * G + gg) * DH + d] = f2bf(s);
     }
-    if constexpr (kFlags) dep_signal_cta(done_ctr);
 }
 
-template <bool kFlags>
-__global__ void swiglu_kernel(SwigluCore a, DepFlag wait, unsigned* done_ctr) {
+// ------------------------------------------------------------------------------------------------
+// SwiGLU on a plain fp32 GEMM result (prefill, codec): 4 consecutive features per thread where aligned
+// ------------------------------------------------------------------------------------------------
+__global__ void swiglu_kernel(SwigluArgs a) {
     pdl_launch_dependents();
-    if constexpr (kFlags) dep_wait_cta(wait);
-    else pdl_wait();
+    pdl_wait();
     const int row = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.I) {
-        const int rws[2] = {row, row}, fts[2] = {i, a.I + i};
-        const bool ok[2] = {true, true};
-        float y[2];
-        sum_parts_n<2>(a.parts, rws, fts, ok, y, a.parts.max_parts > 0 ? a.parts.max_parts : 1);
-        const float g = rbf(y[0]), c = rbf(y[1]);
-        const float s = rbf(g / (1.f + expf(-g)));
-        a.h[static_cast<size_t>(row) * a.I + i] = f2bf(s * c);
-    }
-    if constexpr (kFlags) dep_signal_cta(done_ctr);
+    if (i >= a.I) return;
+    const float* y = a.y + static_cast<size_t>(row) * a.ld;
+    const int gi = a.interleaved ? w13_gate_row(i) : i;
+    const int ui = a.interleaved ? gi + 16 : a.I + i;
+    const float g = rbf(y[gi]), c = rbf(y[ui]);
+    const float s = rbf(g / (1.f + expf(-g)));
+    a.h[static_cast<size_t>(row) * a.I + i] = f2bf(s * c);
 }
 
-// Vectorised SwiGLU (I % 4 == 0): 4 consecutive features per thread, 16-byte partial loads.
-template <bool kFlags>
-__global__ void swiglu4_kernel(SwigluCore a, DepFlag wait, unsigned* done_ctr) {
+__global__ void swiglu4_kernel(SwigluArgs a) {
     pdl_launch_dependents();
-    if constexpr (kFlags) dep_wait_cta(wait);
-    else pdl_wait();
+    pdl_wait();
     const int row = blockIdx.y;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i < a.I) {
-        const int maxp = a.parts.max_parts > 0 ? a.parts.max_parts : 1;
-        const int npg = a.parts.nparts ? __ldg(a.parts.nparts + (i >> 7)) : 1;
-        const int npu = a.parts.nparts ? __ldg(a.parts.nparts + ((a.I + i) >> 7)) : 1;
-        const float4* pg = reinterpret_cast<const float4*>(a.parts.ws + static_cast<size_t>(row) * a.parts.ld + i);
-        const float4* pu = reinterpret_cast<const float4*>(a.parts.ws + static_cast<size_t>(row) * a.parts.ld + a.I + i);
-        const size_t ss4 = static_cast<size_t>(a.parts.slot_stride) >> 2;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f), u = g;
-        const float4 z = g;
-        for (int q = 0; q < maxp; q += 4) {
-            float4 tg[4], tu[4];
+    if (i >= a.I) return;
+    const float* y = a.y + static_cast<size_t>(row) * a.ld;
+    // 4 consecutive h features never straddle a 16-feature interleave group
+    const int gi = a.interleaved ? w13_gate_row(i) : i;
+    const int ui = a.interleaved ? gi + 16 : a.I + i;
+    const float4 g4 = *reinterpret_cast<const float4*>(y + gi);
+    const float4 u4 = *reinterpret_cast<const float4*>(y + ui);
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, uv[4] = {u4.x, u4.y, u4.z, u4.w};
+    float h[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                tg[k] = (q + k < npg) ? pg[static_cast<size_t>(q + k) * ss4] : z;
-                tu[k] = (q + k < npu) ? pu[static_cast<size_t>(q + k) * ss4] : z;
-            }
-            if (q < npg) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { g.x += tg[k].x; g.y += tg[k].y; g.z += tg[k].z; g.w += tg[k].w; }
-            }
-            if (q < npu) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { u.x += tu[k].x; u.y += tu[k].y; u.z += tu[k].z; u.w += tu[k].w; }
-            }
-        }
-        const float gv[4] = {g.x, g.y, g.z, g.w}, uv[4] = {u.x, u.y, u.z, u.w};
-        float h[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float gg = rbf(gv[c]), cc = rbf(uv[c]);
-            const float sl = rbf(gg / (1.f + expf(-gg)));
-            h[c] = sl * cc;
-        }
-        uint2 o;
-        o.x = pack_bf2(h[0], h[1]);
-        o.y = pack_bf2(h[2], h[3]);
-        *reinterpret_cast<uint2*>(a.h + static_cast<size_t>(row) * a.I + i) = o;
+    for (int c = 0; c < 4; ++c) {
+        const float gg = rbf(gv[c]), cc = rbf(uv[c]);
+        const float sl = rbf(gg / (1.f + expf(-gg)));
+        h[c] = sl * cc;
     }
-    if constexpr (kFlags) dep_signal_cta(done_ctr);
+    uint2 o;
+    o.x = pack_bf2(h[0], h[1]);
+    o.y = pack_bf2(h[2], h[3]);
+    *reinterpret_cast<uint2*>(a.h + static_cast<size_t>(row) * a.I + i) = o;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -545,11 +517,9 @@ __device__ __forceinline__ ArgMax block_argmax(ArgMax x, ArgMax* red) {
     return red[32];
 }
 
-template <bool kFlags>
-__global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleCore a, DepFlag wait, SlotCtl ctl) {
+__global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
     pdl_launch_dependents();
-    if constexpr (kFlags) dep_wait_cta(wait);
-    else pdl_wait();
+    pdl_wait();
     __shared__ float lg[kSampleMaxN];
     __shared__ ArgMax red[33];
     __shared__ float fred[33];
@@ -558,6 +528,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleCore a, De
     __shared__ float sel_cum[kSelCap];
     __shared__ int s_nsel;
     __shared__ int s_choice[2];
+    const SlotCtl& ctl = a.ctl;
     const int row = blockIdx.x;
     const int slot = a.row_slot ? a.row_slot[row] : row;
     const int n = a.n;
@@ -567,8 +538,9 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleCore a, De
     const float top_p = per_slot ? ctl.top_p[slot] : a.top_p;
     const int top_k = per_slot ? ctl.top_k[slot] : a.top_k;
     const unsigned long long seed = per_slot ? ctl.seed[slot] : a.seed;
+    const float* src = a.logits + static_cast<size_t>(row) * a.ld;
     for (int e = threadIdx.x; e < n; e += kSampleThreads) {
-        const float v = rbf(sum_parts(a.parts, row, e));
+        const float v = src[e];
         lg[e] = v;
         if (a.logits_out) a.logits_out[static_cast<size_t>(slot) * n + e] = v;
     }
@@ -593,14 +565,15 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleCore a, De
         const float p_lim = two ? fmaxf(top_p, 0.9f) : top_p;
         int kcap = top_k < n ? top_k : n;
         if (kcap > kSelCap) kcap = kSelCap;
-        float cum = 0.f;
+        float cumf = 0.f;  // torch.cumsum over bf16 accumulates in fp32 and rounds each output
         int nsel = 0;
         for (int r = 0; r < kcap; ++r) {
             ArgMax x{-INFINITY, 0x7fffffff};
             for (int e = threadIdx.x; e < n; e += kSampleThreads) x = better(x, ArgMax{lg[e], e});
             x = block_argmax(x, red);
             const float pr = rbf(expf(x.v - m) / z);
-            cum = rbf(cum + pr);
+            cumf += pr;
+            const float cum = rbf(cumf);
             if (threadIdx.x == 0) {
                 sel_v[r] = x.v;
                 sel_i[r] = x.i;
@@ -633,16 +606,29 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleCore a, De
             const unsigned long long off =
                 per_slot ? static_cast<unsigned long long>(ctl.n_out[slot]) : (a.rng_offset ? *a.rng_offset : 0ull);
             const uint32_t lane_id = per_slot ? 0u : static_cast<uint32_t>(slot);
+            const int draw = a.draw_id * 2 + w;
+            const float* noise = (a.noise_u != nullptr && slot == 0)
+                                     ? a.noise_u + (static_cast<size_t>(off) * a.noise_draws + draw) * a.noise_ld
+                                     : nullptr;
             ArgMax best{-INFINITY, 0x7fffffff};
             for (int r = lane; r < ns; r += 32) {
                 const float pr = rbf(expf(rbf(sel_v[r] / Tc) - mx) / zz);
-                uint32_t rnd[4];
-                philox4x32(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32),
-                           static_cast<uint32_t>(off), static_cast<uint32_t>(off >> 32), lane_id,
-                           static_cast<uint32_t>((a.draw_id * 2 + w) * kSelCap + r), rnd);
-                const float u = (static_cast<float>(rnd[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-                const float q = -logf(u);
-                best = better(best, ArgMax{pr / q, r});
+                const int e = sel_i[r];
+                // torch.argmax returns the first maximum in vocabulary order: ties break on the token id
+                const int key = a.slow ? (e < a.n_sem ? a.sem_begin + e : a.im_end_id) : e;
+                float score;
+                if (noise != nullptr) {
+                    const float q = rbf(-logf(noise[e]));  // -log(U) as a bf16 tensor (inference.py:43-46)
+                    score = rbf(pr / q);
+                } else {
+                    uint32_t rnd[4];
+                    philox4x32(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32),
+                               static_cast<uint32_t>(off), static_cast<uint32_t>(off >> 32), lane_id,
+                               static_cast<uint32_t>(draw * kSelCap + r), rnd);
+                    const float u = (static_cast<float>(rnd[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                    score = pr / -logf(u);
+                }
+                best = better(best, ArgMax{score, key * kSelCap + r});
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -651,7 +637,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleCore a, De
                 y.i = __shfl_xor_sync(0xffffffffu, best.i, o);
                 best = better(best, y);
             }
-            if (lane == 0) s_choice[w] = sel_i[best.i];
+            if (lane == 0) s_choice[w] = sel_i[best.i % kSelCap];
         }
         __syncthreads();
         if (!two && threadIdx.x == 0) s_choice[1] = s_choice[0];
@@ -689,9 +675,10 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleCore a, De
     }
 }
 
-__global__ void frame_end_kernel(FrameEndCore a, SlotCtl ctl) {
+__global__ void frame_end_kernel(FrameEndArgs a) {
     pdl_launch_dependents();
     pdl_wait();
+    const SlotCtl& ctl = a.ctl;
     const int row = blockIdx.x;
     const int slot = a.row_slot ? a.row_slot[row] : row;
     if (!slot_live(ctl, slot)) return;
@@ -713,88 +700,43 @@ __global__ void frame_end_kernel(FrameEndCore a, SlotCtl ctl) {
             a.pos[slot] = a.pos[slot] + 1;
     }
 }
-__global__ void step_inc_kernel(unsigned long long* step) {     pdl_launch_dependents();
-    pdl_wait();
-*step += 1; }
-
-__global__ void gather_rows_kernel(const __nv_bfloat16* src, const int* idx, __nv_bfloat16* dst, int D) {
+__global__ void step_inc_kernel(unsigned long long* step) {
     pdl_launch_dependents();
     pdl_wait();
-    const int row = blockIdx.x;
-    const size_t s = static_cast<size_t>(idx[row]) * D, d = static_cast<size_t>(row) * D;
-    for (int e = threadIdx.x; e < D; e += blockDim.x) dst[d + e] = src[s + e];
+    *step += 1;
 }
 
 }  // namespace
 
 int launch_embed(const EmbedArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
-    FSB_LAUNCH(embed_kernel, dim3(a.rows), dim3(256), 0, st, a, sqrtf(static_cast<float>(a.C + 1)));
+    FSB_CHECK(a.D % 4 == 0 && a.D <= kSsqTile * kSsqRowStride, "embed: D=%d unsupported", a.D);
+    FSB_LAUNCH(embed_kernel, dim3(a.rows), dim3(kRowThreads), 0, st, a, sqrtf(static_cast<float>(a.C + 1)));
     return 0;
 }
 
-int launch_resid_norm(const ResidNormArgs& a, cudaStream_t st) { return launch_resid_norm_g(a, 1, st); }
-
-static int rn_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("FSB_RN_VARIANT");
-        v = e ? atoi(e) : 2;  // 0: scalar kernel, 1/2/3: vectorised with 8/16/4 slots per round (6.21 / 5.80 / 5.76 / 6.11 ms per frame)
-    }
-    return v;
+int launch_rows(const RowsArgs& a, cudaStream_t st) {
+    if (a.rows <= 0) return 0;
+    FSB_CHECK(a.D % 4 == 0 && a.D <= kSsqTile * kSsqRowStride, "rows: D=%d unsupported", a.D);
+    FSB_CHECK(a.norm_w == nullptr || a.ssq_in != nullptr, "rows: the norm needs the input's sum of squares");
+    FSB_LAUNCH(rows_kernel, dim3(a.rows), dim3(kRowThreads), 0, st, a);
+    return 0;
 }
 
-int launch_resid_norm_g(const ResidNormArgs& a, int gather_stride, cudaStream_t st) {
+int launch_resid_norm(const ResidNormArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
     FSB_CHECK(a.D <= kRnThreads * kRnMaxPer, "resid_norm: D=%d too large", a.D);
-    const bool fl = a.wait.ctr != nullptr || a.done_ctr != nullptr;
-    const ResidNormCore core = static_cast<ResidNormCore>(a);
-    const int var = rn_variant();
-    const bool vec_ok = var > 0 && (a.D & 3) == 0 && (!a.parts.ws || ((a.parts.ld & 3) == 0 && (a.parts.slot_stride & 3) == 0));
-    if (vec_ok) {
-        const int G = a.D >> 2;
-#define FSB_RN4(GP_, U_, T_)                                                                                        \
-    do {                                                                                                            \
-        if (fl)                                                                                                     \
-            FSB_LAUNCH((resid_norm4_kernel<true, GP_, U_>), dim3(a.rows), dim3(T_), 0, st, core, gather_stride,     \
-                       a.wait, a.done_ctr);                                                                         \
-        else                                                                                                        \
-            FSB_LAUNCH((resid_norm4_kernel<false, GP_, U_>), dim3(a.rows), dim3(T_), 0, st, core, gather_stride,    \
-                       a.wait, a.done_ctr);                                                                         \
-    } while (0)
-        if (G <= kRn4MaxThreads) {
-            const int T = ((G + 31) / 32) * 32;
-            if (var == 2) FSB_RN4(1, 16, T);
-            else if (var == 3) FSB_RN4(1, 4, T);
-            else FSB_RN4(1, 8, T);
-        } else {
-            FSB_RN4(2, 4, 512);
-        }
-#undef FSB_RN4
-        return 0;
-    }
-    if (fl)
-        FSB_LAUNCH(resid_norm_kernel<true>, dim3(a.rows), dim3(kRnThreads), 0, st, core, gather_stride, a.wait, a.done_ctr);
-    else
-        FSB_LAUNCH(resid_norm_kernel<false>, dim3(a.rows), dim3(kRnThreads), 0, st, core, gather_stride, a.wait, a.done_ctr);
-    return 0;
-}
-
-int launch_linear_out(const LinearOutArgs& a, cudaStream_t st) {
-    if (a.rows <= 0) return 0;
-    FSB_LAUNCH(linear_out_kernel, dim3(cdiv(a.N, 256), a.rows), dim3(256), 0, st, a);
+    const bool vec = (a.D & 3) == 0 && (a.y == nullptr || ((a.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0));
+    if (vec) FSB_LAUNCH(resid_norm4_kernel, dim3(a.rows), dim3(kRn4Threads), 0, st, a);
+    else FSB_LAUNCH(resid_norm_kernel, dim3(a.rows), dim3(kRnThreads), 0, st, a);
     return 0;
 }
 
 int launch_qkv_prep(const QkvPrepArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
     FSB_CHECK(a.Dh % 64 == 0 && a.Dh <= 256, "qkv_prep: head_dim %d unsupported", a.Dh);
-    if (a.wait.ctr != nullptr)
-        FSB_LAUNCH(qkv_prep_kernel<true>, dim3(a.rows, a.H + 2 * a.Hkv), dim3(a.Dh / 2), 0, st,
-                   static_cast<QkvPrepCore>(a), a.wait);
-    else
-        FSB_LAUNCH(qkv_prep_kernel<false>, dim3(a.rows, a.H + 2 * a.Hkv), dim3(a.Dh / 2), 0, st,
-                   static_cast<QkvPrepCore>(a), a.wait);
+    FSB_CHECK((a.ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 7) == 0, "qkv_prep: misaligned GEMM result");
+    FSB_LAUNCH(qkv_prep_kernel, dim3(a.rows, a.H + 2 * a.Hkv), dim3(a.Dh / 2), 0, st, a);
     return 0;
 }
 
@@ -806,22 +748,19 @@ static int launch_attn_t(const AttnArgs& a, cudaStream_t st) {
                          static_cast<size_t>(kAttnWarps) * G * DH) * sizeof(float);
     FSB_CHECK(smem <= 200 * 1024, "attention: context %d too long for the shared-memory score buffer", lcap);
     const float scale = 1.0f / sqrtf(static_cast<float>(DH));
-    if (a.done_ctr != nullptr)
-        FSB_LAUNCH((attn_kernel<DH, G, true>), dim3(a.Hkv, a.rows), dim3(kAttnThreads), smem, st,
-                   static_cast<AttnCore>(a), scale, lcap, a.done_ctr);
-    else
-        FSB_LAUNCH((attn_kernel<DH, G, false>), dim3(a.Hkv, a.rows), dim3(kAttnThreads), smem, st,
-                   static_cast<AttnCore>(a), scale, lcap, a.done_ctr);
+    FSB_LAUNCH((attn_kernel<DH, G>), dim3(a.Hkv, a.rows), dim3(kAttnThreads), smem, st, a, scale, lcap);
     return 0;
 }
 
 int attn_init() {
-#define FSB_ATTN_ATTR(DH_, G_)                                                                                       \
-    FSB_CUDA(cudaFuncSetAttribute(attn_kernel<DH_, G_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-    FSB_CUDA(cudaFuncSetAttribute(attn_kernel<DH_, G_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    static bool done = false;
+    if (done) return 0;
+#define FSB_ATTN_ATTR(DH_, G_) \
+    FSB_CUDA(cudaFuncSetAttribute(attn_kernel<DH_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     FSB_ATTN_ATTR(128, 1) FSB_ATTN_ATTR(128, 2) FSB_ATTN_ATTR(128, 4) FSB_ATTN_ATTR(128, 8)
     FSB_ATTN_ATTR(64, 1) FSB_ATTN_ATTR(64, 2) FSB_ATTN_ATTR(64, 4) FSB_ATTN_ATTR(64, 8)
 #undef FSB_ATTN_ATTR
+    done = true;
     return 0;
 }
 
@@ -838,23 +777,11 @@ int launch_attn(const AttnArgs& a, cudaStream_t st) {
     return 1;
 }
 
-int swiglu_ctas(int rows, int I) {
-    const bool vec = (I & 3) == 0 && rn_variant() > 0;  // partial workspaces are always 16-byte aligned in the engine
-    return rows * (vec ? cdiv(I, 1024) : cdiv(I, 256));
-}
-
 int launch_swiglu(const SwigluArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
-    const bool fl = a.wait.ctr != nullptr || a.done_ctr != nullptr;
-    const SwigluCore core = static_cast<SwigluCore>(a);
-    const bool vec = (a.I & 3) == 0 && (a.parts.ld & 3) == 0 && (a.parts.slot_stride & 3) == 0 && rn_variant() > 0;
-    if (vec) {
-        if (fl) FSB_LAUNCH(swiglu4_kernel<true>, dim3(cdiv(a.I, 1024), a.rows), dim3(256), 0, st, core, a.wait, a.done_ctr);
-        else FSB_LAUNCH(swiglu4_kernel<false>, dim3(cdiv(a.I, 1024), a.rows), dim3(256), 0, st, core, a.wait, a.done_ctr);
-        return 0;
-    }
-    if (fl) FSB_LAUNCH(swiglu_kernel<true>, dim3(cdiv(a.I, 256), a.rows), dim3(256), 0, st, core, a.wait, a.done_ctr);
-    else FSB_LAUNCH(swiglu_kernel<false>, dim3(cdiv(a.I, 256), a.rows), dim3(256), 0, st, core, a.wait, a.done_ctr);
+    const bool vec = (a.I & 3) == 0 && (a.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0;
+    if (vec) FSB_LAUNCH(swiglu4_kernel, dim3(cdiv(a.I, 1024), a.rows), dim3(256), 0, st, a);
+    else FSB_LAUNCH(swiglu_kernel, dim3(cdiv(a.I, 256), a.rows), dim3(256), 0, st, a);
     return 0;
 }
 
@@ -862,25 +789,13 @@ int launch_sample(const SampleArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
     FSB_CHECK(a.n > 0 && a.n <= kSampleMaxN, "sample: n=%d out of range", a.n);
     FSB_CHECK(a.ctl.state != nullptr || a.top_k >= 1, "sample: top_k must be >= 1");
-    if (a.wait.ctr != nullptr)
-        FSB_LAUNCH(sample_kernel<true>, dim3(a.rows), dim3(kSampleThreads), 0, st, static_cast<SampleCore>(a), a.wait,
-                   a.ctl);
-    else
-        FSB_LAUNCH(sample_kernel<false>, dim3(a.rows), dim3(kSampleThreads), 0, st, static_cast<SampleCore>(a), a.wait,
-                   a.ctl);
+    FSB_LAUNCH(sample_kernel, dim3(a.rows), dim3(kSampleThreads), 0, st, a);
     return 0;
 }
 
 int launch_frame_end(const FrameEndArgs& a, cudaStream_t st) {
-    FSB_LAUNCH(frame_end_kernel, dim3(a.rows), dim3(32), 0, st, static_cast<FrameEndCore>(a), a.ctl);
+    FSB_LAUNCH(frame_end_kernel, dim3(a.rows), dim3(32), 0, st, a);
     FSB_LAUNCH(step_inc_kernel, dim3(1), dim3(1), 0, st, a.step);
-    return 0;
-}
-
-int launch_gather_rows(const __nv_bfloat16* src, const int* idx, __nv_bfloat16* dst, int rows, int D,
-                       cudaStream_t st) {
-    if (rows <= 0) return 0;
-    FSB_LAUNCH(gather_rows_kernel, dim3(rows), dim3(256), 0, st, src, idx, dst, D);
     return 0;
 }
 

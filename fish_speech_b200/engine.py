@@ -35,6 +35,20 @@ def rope_table(seq_len: int, n_elem: int, base: float) -> torch.Tensor:
     return torch.stack([cis.real, cis.imag], dim=-1).to(torch.bfloat16)
 
 
+def interleave_w13(w1: torch.Tensor, w3: torch.Tensor) -> torch.Tensor:
+    """Fused gate|up projection in the row order the step GEMM's SwiGLU epilogue expects (include/fishb200.h,
+    d_w13): per 128-row tile t, rows 32w+l (l<16) = w1[64t+16w+l] and rows 32w+16+l = w3[64t+16w+l]; the
+    hidden size is padded to a multiple of 64 with zero rows."""
+    I, D = w1.shape
+    Ip = (I + 63) // 64 * 64
+    if Ip != I:
+        pad = torch.zeros(Ip - I, D, dtype=w1.dtype, device=w1.device)
+        w1, w3 = torch.cat([w1, pad]), torch.cat([w3, pad])
+    g = w1.reshape(Ip // 16, 1, 16, D)
+    u = w3.reshape(Ip // 16, 1, 16, D)
+    return torch.cat([g, u], dim=1).reshape(2 * Ip, D).contiguous()
+
+
 def bf16_round(v: float) -> float:
     """Sampling scalars are bf16 tensors in the reference (inference.py:303-304)."""
     return float(torch.tensor(v, dtype=torch.bfloat16).float())
@@ -77,8 +91,8 @@ class LmEngine:
             L.d_wo = put(sd[f"{prefix}.attention.wo.weight"])
             L.d_bo = put(sd[f"{prefix}.attention.wo.bias"]) if f"{prefix}.attention.wo.bias" in sd else None
             L.d_ffn_norm = put(sd[f"{prefix}.ffn_norm.weight"])
-            # fused gate|up projection: rows [0,I) = w1, rows [I,2I) = w3
-            L.d_w13 = put(torch.cat([sd[f"{prefix}.feed_forward.w1.weight"], sd[f"{prefix}.feed_forward.w3.weight"]], 0))
+            # fused gate|up projection, rows interleaved so that SwiGLU runs in the GEMM epilogue
+            L.d_w13 = put(interleave_w13(sd[f"{prefix}.feed_forward.w1.weight"], sd[f"{prefix}.feed_forward.w3.weight"]))
             L.d_w2 = put(sd[f"{prefix}.feed_forward.w2.weight"])
             return L
 
@@ -163,11 +177,8 @@ class LmEngine:
             "slot_top_p": ((self.max_batch,), "<f4"),
             "slot_top_k": ((self.max_batch,), "<i4"),
             "slot_seed": ((self.max_batch,), "<i8"),
-            "pk_trace": ((1024,), "<i8"),
             "slow_logits": ((self.max_batch, self.head_rows), "<f4"),
             "fast_logits": ((c.num_codebooks, self.max_batch, c.codebook_size), "<f4"),
-            "hidden": ((32 * max(c.dim, c.fast_dim),), "<u2"),
-            "dbg_x": (((c.n_layer + 1) * 32 * c.dim,), "<u2"),
         }
         shape, ts = shapes[name]
         with torch.cuda.device(self.device):
@@ -204,6 +215,16 @@ class LmEngine:
         """Per-slot sampling parameters / stop rule / RNG stream (include/fishb200.h fsb_lm_set_slot_control)."""
         _lib.check(self.lib.fsb_lm_set_slot_control(self.h, int(bool(enable))))
         self.slot_control = bool(enable)
+
+    def set_sampler_noise(self, u: Optional[torch.Tensor]):
+        """Test hook (include/fishb200.h fsb_lm_set_sampler_noise): u fp32 [frames][draws][ld] on the device."""
+        if u is None:
+            self._noise = None
+            _lib.check(self.lib.fsb_lm_set_sampler_noise(self.h, None, 0, 0))
+            return
+        u = u.to(device=self.device, dtype=torch.float32).contiguous()
+        self._noise = u
+        _lib.check(self.lib.fsb_lm_set_sampler_noise(self.h, u.data_ptr(), u.shape[1], u.shape[2]))
 
     def reset(self):
         self._ctx_bound = 0
@@ -271,6 +292,9 @@ class LmEngine:
 
         if os.environ.get("FSB_NO_GRAPH") == "1":  # diagnostic: eager launches instead of graph replays
             use_graph = False
+        if not self.slot_control and self._ctx_bound - 1 + nframes > self.kv_len:
+            raise ValueError(f"decode: {nframes} more frames from position {self._ctx_bound - 1} run past the KV "
+                             f"cache ({self.kv_len} positions)")
         self._grow_bound(self._ctx_bound + nframes)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.fsb_lm_decode(self.h, batch, nframes, C.byref(sp) if sp is not None else None,

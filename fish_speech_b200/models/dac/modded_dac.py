@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import threading
 from dataclasses import dataclass, field
 from typing import Iterator, Optional
 
@@ -113,6 +114,7 @@ class DAC:
         self.latent_dim = cfg.latent_dim
         self._keep: list[torch.Tensor] = []
         self._bufs: dict = {}
+        self._lock = threading.RLock()
         self._rope: dict = {}
         self._sd = {k: v.detach().float() for k, v in state_dict.items()}  # folded on the device they live on
         with torch.cuda.device(self._device):
@@ -358,12 +360,13 @@ class DAC:
         vc = self._buf("tf_v", rows * H * Dh)
         att = self._buf("tf_att", rows * H * Dh)
         hb = self._buf("tf_h", rows * I)
-        key = ("rows", B, T)
-        if key not in self._bufs:
-            seq = torch.arange(B, dtype=torch.int32).repeat_interleave(T)
-            pos = torch.arange(T, dtype=torch.int32).repeat(B)
-            self._bufs[key] = (seq.to(self._device), pos.to(self._device))
-        seq, pos = self._bufs[key]
+        # (sequence, position) of every row: two persistent int32 buffers refilled per call (a per-(B, T) cache
+        # would grow without bound over a dataset-scale bulk encode, where almost every batch has a new shape)
+        seq = self._buf("tf_seq", rows, torch.int32)[:rows]
+        pos = self._buf("tf_pos", rows, torch.int32)[:rows]
+        ar = torch.arange(rows, dtype=torch.int32, device=self._device)
+        torch.div(ar, T, rounding_mode="floor", out=seq)
+        torch.remainder(ar, T, out=pos)
         freqs = self._rope_table(T, Dh, t.rope_base)
         window = t.window_size if t.window_size is not None else 0
         layers = tf["layers"]
@@ -404,7 +407,9 @@ class DAC:
         """modded_dac.py:925-927: codes [B, 1+n_codebooks, T] -> waveform [B, 1, T*frame_length] (fp32).
         Like the reference (rvq.py:354-359) the caller's tensor is clamped in place."""
         cfg = self.cfg
-        with torch.cuda.device(self._device):
+        # one caller at a time per DAC object: the layers share persistent workspaces (the reference's nn.Module
+        # allocates per call and may be driven from two host threads, e.g. TTSInferenceEngine + a batch encoder)
+        with self._lock, torch.cuda.device(self._device):
             indices[:, 0] = torch.clamp(indices[:, 0], max=cfg.semantic_codebook_size - 1)
             indices[:, 1:] = torch.clamp(indices[:, 1:], max=cfg.codebook_size - 1)
             idx = indices.to(device=self._device, dtype=torch.int32).contiguous()
@@ -429,7 +434,7 @@ class DAC:
     @torch.inference_mode()
     def decode(self, z: torch.Tensor) -> torch.Tensor:
         """modded_dac.py:929-946: latent [B, D, T'] (channels first) -> waveform [B, 1, T'*hop]."""
-        with torch.cuda.device(self._device):
+        with self._lock, torch.cuda.device(self._device):
             B, D, Tc = z.shape
             buf = self._buf("dec_zin", B * Tc * D)
             buf[: B * Tc * D].view(B, Tc, D).copy_(z.to(self._device).transpose(1, 2))
@@ -492,7 +497,7 @@ class DAC:
                n_quantizers: Optional[int] = None, **kwargs):
         """modded_dac.py:874-923: audio [B,1,N] or [B,N] -> (codes int64 [B, 1+n_codebooks, T], lens [B])."""
         cfg = self.cfg
-        with torch.cuda.device(self._device):
+        with self._lock, torch.cuda.device(self._device):
             if audio_data.ndim == 2:
                 audio_data = audio_data.unsqueeze(1)
             length = audio_data.shape[-1]

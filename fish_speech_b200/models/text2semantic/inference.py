@@ -78,9 +78,12 @@ def decode_one_token_ar(
         start = int(input_pos[0].item())
         eng.prefill([x[0]], [0], sp, start_pos=[start], do_sample=True)
     else:
+        p0 = int(input_pos.view(-1)[0].item())
+        if p0 >= eng.kv_len:
+            raise ValueError(f"input_pos {p0} is outside the KV cache ({eng.kv_len} positions)")
         eng.buffer("cur_tok")[0].copy_(x[0, :, 0].to(torch.int32))
         eng.buffer("pos")[0:1].copy_(input_pos.to(torch.int32).view(1))
-        eng.set_context_bound(int(input_pos.view(-1)[0].item()) + 1)
+        eng.set_context_bound(p0 + 1)
         win = eng.buffer("ras_window")
         if previous_tokens is not None:
             win[0].copy_(previous_tokens[0].to(torch.int32))
@@ -192,7 +195,11 @@ def generate_batch(
     else:
         max_new_tokens = cfg.max_seq_len - T_max
     eng = _ensure_engine(model, B)
-    max_new_tokens = min(max_new_tokens, eng.max_frames)
+    # the engine's KV cache may be smaller than config.max_seq_len (setup_caches(max_seq_len=...)): never
+    # decode past it
+    if T_max >= eng.kv_len:
+        raise ValueError(f"Input sequence length {T_max} exceeds the KV cache ({eng.kv_len})")
+    max_new_tokens = min(max_new_tokens, eng.max_frames, eng.kv_len - T_max)
     seed = int(sampling_kwargs.get("seed", torch.initial_seed())) & 0x7FFFFFFFFFFFFFFF
     sp = eng.sampling(sampling_kwargs.get("temperature", 1.0), sampling_kwargs.get("top_p", 0.9),
                       int(sampling_kwargs.get("top_k", 30)), seed)
@@ -516,13 +523,25 @@ def serve_requests(model, input_queue: "queue.Queue", max_slots: int, frames_per
             try:
                 batcher.step()
             except Exception as e:
-                # an engine failure ends the worker: every request in flight hears about it instead of hanging
+                # Per-request problems were rejected in submit(); what fails here is the engine itself (e.g. a
+                # poisoned CUDA context). Every request in flight hears about it, and so does everything still
+                # queued or arriving later: the worker keeps answering (with the error) instead of dying with
+                # callers blocked on their response queues.
                 logger.error(traceback.format_exc())
                 for q_ in waiting_queues.values():
                     q_.put(WrappedGenerateResponse(status="error", response=e))
-                raise
+                waiting_queues.clear()
+                while not closing:
+                    item = input_queue.get()
+                    if item is None:
+                        break
+                    item.response_queue.put(WrappedGenerateResponse(status="error", response=e))
+                return
     finally:
-        batcher.close()
+        try:
+            batcher.close()
+        except Exception:  # a failed engine may not reset cleanly; do not mask the original error
+            logger.error(traceback.format_exc())
 
 
 def launch_thread_safe_queue(checkpoint_path, device, precision, compile: bool = False):

@@ -81,7 +81,23 @@ class ContinuousBatcher:
 
     # ------------------------------------------------------------------------------------------
     def submit(self, req: SlotRequest) -> SlotRequest:
+        """Queue a request. Everything that can be wrong with ONE request is rejected here, with a ValueError the
+        caller can hand back to that request alone; what reaches the engine later cannot fail per request."""
         cfg = self.cfg
+        p = req.prompt
+        if not isinstance(p, torch.Tensor) or p.ndim != 2 or p.size(0) != cfg.num_codebooks + 1 or p.size(1) < 1:
+            raise ValueError(f"prompt must be an integer tensor [{cfg.num_codebooks + 1}, T>=1], got "
+                             f"{tuple(p.shape) if isinstance(p, torch.Tensor) else type(p)}")
+        if p.is_floating_point() or p.dtype == torch.bool:
+            raise ValueError(f"prompt must hold integer token ids / codes, got {p.dtype}")
+        # the reference asserts 0 < top_p <= 1 and 0 < temperature < 2 (inference.py:541-542); top_k >= 1 keeps
+        # rank 0 only at 1. The sampler materialises at most 256 ranks: a larger top_k behaves like 256.
+        if not (0.0 < float(req.top_p) <= 1.0):
+            raise ValueError(f"top_p must be in (0, 1], got {req.top_p}")
+        if not (0.0 < float(req.temperature) < 2.0):
+            raise ValueError(f"temperature must be in (0, 2), got {req.temperature}")
+        if int(req.top_k) < 1:
+            raise ValueError(f"top_k must be >= 1, got {req.top_k}")
         T = int(req.prompt.size(1))
         if T >= cfg.max_seq_len:  # inference.py:262-265
             raise ValueError(f"Input sequence length {T} exceeds max_seq_len {cfg.max_seq_len}")

@@ -69,7 +69,10 @@ typedef struct {
     const void* d_wo;         /* [dim, H*Dh] */
     const void* d_bo;         /* optional */
     const void* d_ffn_norm;   /* [dim] */
-    const void* d_w13;        /* [2*I, dim]: rows [0,I) = w1, rows [I,2I) = w3 */
+    const void* d_w13;        /* [ceil(I/64)*128, dim]: w1 and w3 interleaved per 128-row tile so that SwiGLU runs in
+                                 the GEMM epilogue: tile t holds hidden features [64t, 64t+64); inside it, row
+                                 32w + l (l < 16) = w1[64t + 16w + l] and row 32w + 16 + l = w3[64t + 16w + l];
+                                 rows past I are zero (fish_speech_b200.engine.interleave_w13 builds it) */
     const void* d_w2;         /* [dim, I] */
 } fsb_lm_layer;
 
@@ -144,18 +147,22 @@ int fsb_lm_reset(fsb_lm* h, void* stream);
  *   "out_tokens" int32 [max_batch][C+1][max_frames], "n_out" int32 [max_batch], "pos" int32 [max_batch],
  *   "finished" int32 [max_batch], "cur_tok" int32 [max_batch][C+1], "ras_window" int32 [max_batch][10],
  *   the slot-control arrays listed at fsb_lm_set_slot_control,
- *   debug only: "slow_logits" f32 [max_batch][head_rows], "fast_logits" f32 [C][max_batch][codebook_size],
- *   "hidden" bf16 [32][dim], "dbg_x" bf16 [n_layer+1][32][dim] */
+ *   debug only: "slow_logits" f32 [max_batch][head_rows], "fast_logits" f32 [C][max_batch][codebook_size] */
 int fsb_lm_buffer(fsb_lm* h, const char* name, void** d_ptr, size_t* bytes);
 
-/* Measurement hook for bench.py: launch every weight-streaming GEMM of one decode frame `reps` times
- * (no glue kernels); returns the algorithmic weight bytes and launch count of one repetition. */
+/* Measurement hook for bench.py: launch every weight-streaming step GEMM of one decode frame `reps` times
+ * (no attention / sampling kernels; the fused epilogues run and overwrite the decode state, so call it after
+ * the timed generation); returns the algorithmic weight bytes and launch count of one repetition. */
 int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* launches_per_rep,
                        void* stream);
 
-/* Diagnostic: GEMM chain with per-CTA globaltimer stamps {start, after dependency wait, end}; returns the
- * number of launches traced (negative on error is not used: 0 launches means failure). */
-int fsb_lm_trace_gemms(fsb_lm* h, unsigned long long* d_trace, int max_launches, int* grid_out, void* stream);
+/* Test hook for bit-exact parity of the STOCHASTIC sampler with the reference's torch RNG stream
+ * (inference.py:43-46 multinomial_sample_one_no_sync, :114-144 RAS): when d_u != NULL, slot 0 takes the uniforms
+ * of draw d of frame f from d_u[(f * draws_per_frame + d) * ld + candidate] (f = frames produced since
+ * fsb_lm_reset; d = 0 slow token, 1 slow RAS re-draw, 2p fast codebook p; candidate = restricted head row /
+ * code) instead of the library's Philox stream, and forms -log(U) and the scores in bf16 like the reference's
+ * tensors. Pass NULL to restore the Philox stream. */
+int fsb_lm_set_sampler_noise(fsb_lm* h, const float* d_u, int draws_per_frame, int ld);
 
 /* ------------------------------------------------------------------------------------------------
  * Codec ("Firefly VQ-GAN" = modified Descript-DAC) operators

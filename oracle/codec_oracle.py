@@ -395,14 +395,17 @@ def encoder(w: dict, cfg: CodecConfig, x):
     return causal_conv(w, f"encoder.block.{nb + 1}.conv", x)
 
 
-def _vq_encode(w: dict, prefix: str, z):
-    """VectorQuantize.forward (dac/nn/quantize.py): in_proj -> cosine nearest neighbour -> out_proj."""
+def _vq_encode(w: dict, prefix: str, z, scores: Optional[list] = None):
+    """VectorQuantize.forward (dac/nn/quantize.py): in_proj -> cosine nearest neighbour -> out_proj.
+    `scores` (tests): receives -dist [B, T, K], the quantity the reference maximises."""
     z_e = F.conv1d(z, _wn_weight(w, f"{prefix}.in_proj"), w[f"{prefix}.in_proj.bias"])
     B, D, T = z_e.shape
     enc = F.normalize(z_e.permute(0, 2, 1).reshape(B * T, D))
     cb = F.normalize(w[f"{prefix}.codebook.weight"])
     dist = enc.pow(2).sum(1, keepdim=True) - 2 * enc @ cb.t() + cb.pow(2).sum(1, keepdim=True).t()
     idx = (-dist).max(1)[1].reshape(B, T)
+    if scores is not None:
+        scores.append((-dist).reshape(B, T, -1).clone())
     z_q = F.embedding(idx, w[f"{prefix}.codebook.weight"]).transpose(1, 2)
     z_q = F.conv1d(z_q, _wn_weight(w, f"{prefix}.out_proj"), w[f"{prefix}.out_proj.bias"])
     return z_q, idx
@@ -417,11 +420,12 @@ def quantizer_encode(w: dict, cfg: CodecConfig, z, trace: Optional[dict] = None)
     z = window_transformer(w, "quantizer.pre_module", cfg.quant_tfm, z)
     if trace is not None:
         trace["pre"] = z.clone()
-    zq, sem = _vq_encode(w, "quantizer.semantic_quantizer.quantizers.0", z)
+    scores = trace.setdefault("vq_scores", []) if trace is not None else None
+    zq, sem = _vq_encode(w, "quantizer.semantic_quantizer.quantizers.0", z, scores)
     residual = z - zq
     codes = [sem]
     for i in range(cfg.n_codebooks):
-        zq_i, idx = _vq_encode(w, f"quantizer.quantizer.quantizers.{i}", residual)
+        zq_i, idx = _vq_encode(w, f"quantizer.quantizer.quantizers.{i}", residual, scores)
         residual = residual - zq_i
         codes.append(idx)
     return torch.stack(codes, dim=1)

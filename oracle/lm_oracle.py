@@ -357,6 +357,9 @@ def decode_one_token_ar(st: LMState, x, input_pos, temperature, top_p, top_k: in
     if previous_tokens is not None:
         in_window = (previous_tokens[0] == main).any()
         is_sem = (main >= cfg.semantic_begin_id) & (main <= cfg.semantic_end_id)
+        if trace is not None:
+            trace["ras_hit"] = bool(in_window & is_sem)
+            trace["ras_changed"] = bool(in_window & is_sem) and int(main_high) != int(main)
         main = torch.where(in_window & is_sem, main_high, main)
     if trace is not None:
         trace["slow_logits"] = biased[0, -1].float().clone()

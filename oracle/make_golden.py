@@ -33,6 +33,9 @@ LM_CASES = [
     ("lm_tiny_proj", dict(fast_dim=128, fast_n_head=2, fast_n_local_heads=1, fast_head_dim=64, fast_intermediate_size=256, attention_qk_norm=False,
                           fast_attention_qk_norm=True, norm_fastlayer_input=False,
                           scale_codebook_embeddings=False), 13, 8.0, 10, 8, 1, 0.7, 0.7),
+    # stochastic decode that exercises the RAS substitution (inference.py:114-144): a peaky 96-token semantic head
+    # repeats tokens inside the 10-frame window, so the high-temperature re-draw replaces the main token
+    ("lm_tiny_ras", {}, 16, 2.0, 9, 24, 30, 0.7, 0.8),
     ("lm_tiny_bias", dict(attention_qkv_bias=True, attention_o_bias=True, fast_attention_qkv_bias=True,
                           fast_attention_o_bias=True, n_local_heads=2, fast_n_local_heads=4), 14, 8.0, 16, 8, 1, 0.7, 0.7),
 ]
@@ -98,12 +101,18 @@ def run_lm_case(name, over, seed, head_gain, T, n, top_k, temp, top_p):
             rng_seed += 1000
             continue
         break
+    extra = {}
+    if name == "lm_tiny_ras":
+        extra = dict(ras_hits=sum(bool(t.get("ras_hit")) for t in traces),
+                     ras_changed=sum(bool(t.get("ras_changed")) for t in traces))
+        assert extra["ras_changed"] >= 5, "the RAS fixture must exercise the substitution"
     np.savez_compressed(
         GOLD / f"{name}.npz",
         config=np.array(repr(over)), weight_seed=wseed, head_gain=head_gain, prompt=prompt.numpy(),
         new_frames=n, top_k=top_k, temperature=temp, top_p=top_p, rng_seed=rng_seed,
         ref_tokens=ref.numpy(),
         ref_slow_logits=torch.stack([t["slow_logits"] for t in traces]).numpy().astype(np.float32),
+        **extra,
     )
     print(f"{name}: reference == oracle, {ref.shape[1] - T} frames -> {GOLD / (name + '.npz')}")
 

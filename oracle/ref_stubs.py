@@ -179,8 +179,11 @@ class FakeTokenizer:
         return self._im_end
 
 
-def reference_lm(cfg, weights, max_batch=1):
-    """Build the reference DualARTransformer with the oracle's config/weights (bf16, CPU)."""
+def reference_lm(cfg, weights, max_batch=1, assign=False):
+    """Build the reference DualARTransformer with the oracle's config/weights (bf16, CPU).
+    assign=True (full-size models): construct on the meta device and adopt the given tensors as the parameters
+    (nn.Module.load_state_dict(assign=True)) instead of allocating + initialising 4.5 G fp32 parameters first;
+    the non-persistent buffers are then rebuilt with the reference's own precompute_freqs_cis."""
     install()
     from fish_speech.models.text2semantic import llama as ref_llama
 
@@ -198,11 +201,19 @@ def reference_lm(cfg, weights, max_batch=1):
         fast_attention_qkv_bias=cfg.fast_attention_qkv_bias, fast_attention_qk_norm=cfg.fast_attention_qk_norm,
         fast_attention_o_bias=cfg.fast_attention_o_bias, norm_fastlayer_input=cfg.norm_fastlayer_input,
     )
-    model = ref_llama.DualARTransformer(args)
+    if assign:
+        with torch.device("meta"):
+            model = ref_llama.DualARTransformer(args)
+    else:
+        model = ref_llama.DualARTransformer(args)
     sd = {}
     for k, v in weights.items():
         sd[k] = v
-    missing, unexpected = model.load_state_dict(sd, strict=False)
+    missing, unexpected = model.load_state_dict(sd, strict=False, assign=assign)
+    if assign:
+        model.freqs_cis = ref_llama.precompute_freqs_cis(args.max_seq_len, args.head_dim, args.rope_base)
+        model.causal_mask = torch.tril(torch.ones(args.max_seq_len, args.max_seq_len, dtype=torch.bool))
+        model.fast_freqs_cis = ref_llama.precompute_freqs_cis(args.num_codebooks, args.fast_head_dim, args.rope_base)
     missing = [m for m in missing if "freqs" not in m and "causal" not in m]
     assert not missing and not unexpected, (missing, unexpected)
     model = model.to(dtype=torch.bfloat16).eval()

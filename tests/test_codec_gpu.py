@@ -109,23 +109,57 @@ def test_indices_clamped_in_place_like_reference(tiny):
     assert codes[0, 0, 0].item() == cfg.semantic_codebook_size - 1 and codes[0, 2, 3].item() == cfg.codebook_size - 1
 
 
+# ---- DAC.encode: integer codes -------------------------------------------------------------------
+# The CUDA encoder keeps activations in bf16 (fp32 accumulation); the reference's CLI path is fp32. A cosine
+# nearest-neighbour search over 4096 / 1024 eight-dimensional codewords amplifies that rounding noise into a
+# different index wherever the best two candidates are closer than the noise. Parity bar: codes are IDENTICAL
+# except where the GPU's choice is a near-tie under the ORACLE's own fp32 scores: at the first residual stage
+# where a frame's code differs, score_oracle(best) - score_oracle(GPU's code) <= VQ_EPS (scores are
+# 2*cos - 2 in [-4, 0]); later stages of that frame quantise a different residual and are not comparable.
+VQ_EPS = 0.05
+
+
+def vq_first_mismatches(scores, ref_codes, got_codes):
+    """[(stage, oracle score gap)] for every frame whose codes differ, taken at its first differing stage."""
+    B, S, T = ref_codes.shape
+    out = []
+    for b in range(B):
+        for t in range(T):
+            for s_ in range(S):
+                r, g = int(ref_codes[b, s_, t]), int(got_codes[b, s_, t])
+                if r != g:
+                    sc = scores[s_][b, t]
+                    out.append((s_, float(sc[r] - sc[g])))
+                    break
+    return out
+
+
+def check_encode_parity(w, cfg, audio, lens, codes, out_lens, what, min_frames_equal=0.0, ref_codes=None):
+    trace = {}
+    o_codes, o_lens = CO.encode(w, cfg, audio, lens, trace=trace)
+    if ref_codes is not None:  # committed output of the real reference: the oracle must reproduce it
+        assert torch.equal(o_codes, ref_codes), f"{what}: oracle != committed reference codes"
+    assert codes.shape == o_codes.shape and codes.dtype == torch.int64
+    assert torch.equal(out_lens, o_lens)
+    mism = vq_first_mismatches(trace["vq_scores"], o_codes, codes)
+    frames = codes.shape[0] * codes.shape[2]
+    worst = max((g for _, g in mism), default=0.0)
+    same = float((codes == o_codes).float().mean())
+    print(f"{what}: {frames - len(mism)}/{frames} frames bit-identical over all {codes.shape[1]} stages, "
+          f"{same:.3f} of all codes identical, {len(mism)} frames diverge at a near-tie, worst oracle score gap {worst:.4f}")
+    assert worst <= VQ_EPS, f"{what}: a differing code is NOT a near-tie: oracle score gap {worst:.4f} > {VQ_EPS} ({mism})"
+    assert frames - len(mism) >= min_frames_equal * frames, f"{what}: only {frames - len(mism)}/{frames} frames identical"
+    return len(mism), worst
+
+
 @pytest.mark.parametrize("B,N", [(1, 2048 * 48), (2, 2048 * 30 + 300), (1, 2048 * 3 + 1)])
 def test_encode_matches_oracle(tiny, B, N):
     cfg, w, dac = tiny
     g = torch.Generator().manual_seed(N)
     audio = 0.1 * torch.randn(B, 1, N, generator=g)
     lens = torch.tensor([N] * B)
-    ref_codes, ref_lens = CO.encode(w, cfg, audio, lens)
     codes, out_lens = dac.encode(audio.cuda(), lens.cuda())
-    codes, out_lens = codes.cpu(), out_lens.cpu()
-    assert codes.shape == ref_codes.shape and codes.dtype == torch.int64
-    assert torch.equal(out_lens, ref_lens)
-    sem = (codes[:, 0] == ref_codes[:, 0]).float().mean().item()
-    allc = (codes == ref_codes).float().mean().item()
-    if codes.shape[-1] >= 20:  # enough frames for a rate to mean something
-        assert sem >= 0.9 and allc >= 0.8, f"semantic {sem:.3f}, all {allc:.3f}"
-    else:
-        assert allc >= 0.5, f"all {allc:.3f}"
+    check_encode_parity(w, cfg, audio, lens, codes.cpu(), out_lens.cpu(), f"encode B={B} N={N}")
 
 
 def test_encode_golden_reference_codes():
@@ -133,11 +167,26 @@ def test_encode_golden_reference_codes():
     cfg = CO.tiny_config()
     w = CO.make_weights(cfg, seed=int(z["weight_seed"]))
     dac = build(cfg, w)
-    codes, lens = dac.encode(torch.from_numpy(z["audio"]).cuda(), torch.from_numpy(z["lens"]).cuda())
-    ref = torch.from_numpy(z["ref_codes"]).long()
-    assert torch.equal(lens.cpu(), torch.from_numpy(z["ref_lens"]))
-    sem = (codes.cpu()[:, 0] == ref[:, 0]).float().mean().item()
-    assert sem >= 0.7, f"semantic codes identical: {sem:.3f}"  # 10 frames only
+    audio, lens = torch.from_numpy(z["audio"]), torch.from_numpy(z["lens"])
+    codes, out_lens = dac.encode(audio.cuda(), lens.cuda())
+    check_encode_parity(w, cfg, audio, lens, codes.cpu(), out_lens.cpu(), "encode tiny golden",
+                        ref_codes=torch.from_numpy(z["ref_codes"]).long())
+
+
+def test_encode_full_size_reference_codes():
+    """Full 391 M-parameter geometry, BASELINE config #1 input (1 s of audio): codes against the committed output
+    of the real reference (`codec_full_1s.npz:ref_codes`), near-tie bounded by the oracle's fp32 scores."""
+    f = GOLD / "codec_full_1s.npz"
+    if not f.exists():
+        pytest.skip("full-size fixture not committed")
+    z = np.load(f)
+    cfg = CO.full_config()
+    w = CO.make_weights(cfg, seed=int(z["weight_seed"]))
+    dac = build(cfg, w)
+    audio, lens = torch.from_numpy(z["audio"]), torch.from_numpy(z["lens"])
+    codes, out_lens = dac.encode(audio.cuda(), lens.cuda())
+    check_encode_parity(w, cfg, audio, lens, codes.cpu(), out_lens.cpu(), "encode full-size golden",
+                        ref_codes=torch.from_numpy(z["ref_codes"]).long())
 
 
 def test_roundtrip_full_size_property():

@@ -366,9 +366,12 @@ def test_extract_vq_spawn_plan():
 
 
 def test_slot_scheduler_worker_reports_engine_failure(monkeypatch):
-    """If the batcher itself fails (a CUDA error, say) every request in flight receives an error response and the
-    worker loop ends instead of leaving callers blocked on their queues."""
+    """If the batcher itself fails (a CUDA error, say) every request in flight receives an error response, and so
+    does every request that arrives afterwards: the worker keeps answering instead of dying with callers blocked on
+    their queues (the reference's worker catches per request and keeps serving, inference.py:748-799). `None` ends it;
+    a close() that fails on the broken engine does not mask anything."""
     import queue as Q
+    import threading
 
     monkeypatch.setattr(inf, "_generate_long_plan", _fake_plan)
 
@@ -376,13 +379,38 @@ def test_slot_scheduler_worker_reports_engine_failure(monkeypatch):
         def step(self):
             raise RuntimeError("device lost")
 
+        def close(self):
+            self.closed = True
+            raise RuntimeError("reset failed too")
+
     fb = Boom(slots=2)
     q, outs = Q.Queue(), [Q.Queue(), Q.Queue()]
     for rq in outs:
         q.put(inf.GenerateRequest(request=dict(text="ab", chunks=1), response_queue=rq))
-    with pytest.raises(RuntimeError):
-        inf.serve_requests(_FakeModel(), q, 2, batcher=fb)
-    assert fb.closed
+    t = threading.Thread(target=inf.serve_requests, args=(_FakeModel(), q, 2), kwargs=dict(batcher=fb), daemon=True)
+    t.start()
     for rq in outs:
-        item = rq.get_nowait()
+        item = rq.get(timeout=20)
         assert item.status == "error" and "device lost" in str(item.response)
+    late = Q.Queue()
+    q.put(inf.GenerateRequest(request=dict(text="late", chunks=1), response_queue=late))
+    item = late.get(timeout=20)
+    assert item.status == "error" and "device lost" in str(item.response)
+    q.put(None)
+    t.join(timeout=20)
+    assert not t.is_alive() and fb.closed
+
+
+def test_continuous_batcher_rejects_bad_requests_up_front():
+    """Per-request errors surface in submit() (so the worker can answer that request alone), not in the engine."""
+    from fish_speech_b200.scheduler import ContinuousBatcher, SlotRequest
+
+    b = ContinuousBatcher(_SchedModel(_FakeEngine(slots=2)), max_slots=2)
+    ok = dict(prompt=torch.zeros(3, 4, dtype=torch.long), max_new_tokens=4)
+    for bad in (dict(top_k=0), dict(top_p=0.0), dict(top_p=1.5), dict(temperature=0.0), dict(temperature=2.0),
+                dict(prompt=torch.zeros(2, 4, dtype=torch.long)), dict(prompt=torch.zeros(3, 4)),
+                dict(prompt=torch.zeros(3, 0, dtype=torch.long))):
+        with pytest.raises(ValueError):
+            b.submit(SlotRequest(**{**ok, **bad}))
+    b.submit(SlotRequest(**ok))
+    assert len(b.waiting) == 1

@@ -29,7 +29,7 @@ def _gen(model, prompt, n, **kw):
     return generate(model=model, prompt=prompt.cuda(), max_new_tokens=n, **kw).cpu()
 
 
-@pytest.mark.parametrize("name", sorted(p.name for p in GOLD.glob("lm_*.npz") if "topk" not in p.name))
+@pytest.mark.parametrize("name", sorted(p.name for p in GOLD.glob("lm_*.npz") if int(np.load(p)["top_k"]) == 1))
 def test_greedy_tokens_match_reference_golden(name):
     """Free-running greedy decode: every token id and codebook index equals the reference's."""
     cfg, w, z = load_golden(GOLD / name)
@@ -41,16 +41,47 @@ def test_greedy_tokens_match_reference_golden(name):
     assert torch.equal(got.to(torch.int32), ref), f"first mismatch at {(got != ref).nonzero()[:4].tolist()}"
 
 
-@pytest.mark.parametrize("flag", ["FSB_FLAGS", "FSB_PERSISTENT", "FSB_FUSED_ATTN"])
-def test_optin_decode_variants_match_reference_golden(flag, monkeypatch):
-    """The opt-in decode-chain experiments (device-side dependency flags, persistent stack kernel, fused
-    prep+attention) must produce the reference's tokens too."""
-    monkeypatch.setenv(flag, "1")
-    cfg, w, z = load_golden(GOLD / "lm_tiny_greedy.npz")
+def _reference_uniforms(cfg, rng_seed: int, frames: int, head_rows: int) -> torch.Tensor:
+    """The uniforms torch.rand produced during the recorded reference run, in the reference's order
+    (multinomial_sample_one_no_sync, inference.py:43-46, called by sample() :86-93): per frame one [vocab] draw for
+    the main token, one [vocab] draw for the RAS re-draw (:114-131, drawn even when unused), then one
+    [codebook_size] draw per fast codebook 1..C-1 (:160-174); all in the probs dtype (bf16).  Laid out as the
+    sampler hook expects: [frame][2 * draw_id + which][restricted candidate]."""
+    C = cfg.num_codebooks
+    u = torch.full((frames, 2 * C, max(head_rows, cfg.codebook_size)), 0.5)
+    torch.manual_seed(rng_seed)
+    for f in range(frames):
+        for d in (0, 1):
+            r = torch.rand(cfg.vocab_size, dtype=torch.bfloat16).float()
+            u[f, d, : head_rows - 1] = r[cfg.semantic_begin_id: cfg.semantic_end_id + 1]
+            u[f, d, head_rows - 1] = r[cfg.im_end_id]
+        for p in range(1, C):
+            u[f, 2 * p, : cfg.codebook_size] = torch.rand(cfg.codebook_size, dtype=torch.bfloat16).float()
+    return u
+
+
+@pytest.mark.parametrize("name", ["lm_tiny_topk.npz", "lm_tiny_ras.npz"])
+def test_stochastic_decode_replays_reference_rng(name):
+    """top-k / top-p / temperature sampling AND the RAS substitution, bit-exact: the sampler is fed the very
+    uniforms torch's generator produced in the recorded run of the real reference (debug hook
+    fsb_lm_set_sampler_noise) and must emit the reference's token ids and codes for every frame.
+    lm_tiny_ras repeats tokens inside the 10-frame window, so the high-temperature re-draw replaces the main
+    token in >= 5 frames (stored in the fixture)."""
+    cfg, w, z = load_golden(GOLD / name)
     model = build_model(cfg, w)
-    got = _gen(model, torch.from_numpy(z["prompt"]), int(z["new_frames"]), temperature=float(z["temperature"]),
-               top_p=float(z["top_p"]), top_k=int(z["top_k"]))
-    assert torch.equal(got.to(torch.int32), torch.from_numpy(z["ref_tokens"]))
+    eng = model.engine
+    n = int(z["new_frames"])
+    if "ras" in name:
+        assert int(z["ras_changed"]) >= 5
+    eng.set_sampler_noise(_reference_uniforms(cfg, int(z["rng_seed"]), n, eng.head_rows))
+    try:
+        got = _gen(model, torch.from_numpy(z["prompt"]), n, temperature=float(z["temperature"]),
+                   top_p=float(z["top_p"]), top_k=int(z["top_k"]))
+    finally:
+        eng.set_sampler_noise(None)
+    ref = torch.from_numpy(z["ref_tokens"])
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert torch.equal(got.to(torch.int32), ref), f"first mismatch at {(got != ref).nonzero()[:4].tolist()}"
 
 
 def test_prefill_and_decode_logits_teacher_forced():
