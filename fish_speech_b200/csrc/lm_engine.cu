@@ -800,6 +800,39 @@ int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* l
     return 0;
 }
 
+int fsb_lm_copy_kv(fsb_lm* h, int src_slot, int dst_slot, int n_pos, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    FSB_CHECK(h != nullptr, "copy_kv: null handle");
+    Stack& s = h->slow;
+    FSB_CHECK(n_pos >= 0 && n_pos <= s.S, "copy_kv: n_pos=%d outside the KV cache (%d)", n_pos, s.S);
+    FSB_TRY(launch_kv_copy(s.kcache, s.nl, h->cfg.max_batch, s.Hkv, s.S, s.Dh, src_slot, dst_slot, n_pos, st));
+    FSB_TRY(launch_kv_copy(s.vcache, s.nl, h->cfg.max_batch, s.Hkv, s.S, s.Dh, src_slot, dst_slot, n_pos, st));
+    return 0;
+}
+
+int fsb_lm_trace_step_gemms(fsb_lm* h, unsigned long long* d_trace, int max_launches, int* grid_out, void* stream) {
+    // Diagnostic: the four step GEMMs of the first slow layers, each CTA recording globaltimer stamps
+    // (lm_gemm.cuh StepGemmParams::trace): shows where a launch spends its time and which CTAs share an SM.
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Stack& s = h->slow;
+    int id = 0, grid = 0;
+    for (int l = 0; l < s.nl && id + 4 <= max_launches; ++l) {
+        const StepGemmPlan* plans[4] = {&s.dec[l].qkv, &s.dec[l].wo, &s.dec[l].w13, &s.dec[l].w2};
+        for (int k = 0; k < 4; ++k) {
+            StepGemmPlan q = *plans[k];
+            grid = std::max(grid, static_cast<int>(q.grid.x));
+            q.p.rows = h->cfg.max_batch;
+            q.p.row_seq = h->iota;
+            q.p.row_pos = h->pos;
+            q.p.trace = d_trace + static_cast<size_t>(id++) * 8 * 512;  // 512 CTA records per launch
+            FSB_CHECK(q.grid.x <= 512, "trace: grid too large");
+            FSB_TRY(step_gemm_launch(q, st));
+        }
+    }
+    if (grid_out) *grid_out = grid;
+    return id;
+}
+
 int fsb_lm_set_context_bound(fsb_lm* h, int max_positions) {
     // The attention kernel keeps one fp32 score per live position in shared memory; sizing that buffer by
     // the KV capacity would cap max_seq_len at ~12k. The host knows an upper bound of every slot's length

@@ -7,6 +7,8 @@
 #include "lm_gemm.cuh"
 #include "umma.cuh"
 
+#include <stdlib.h>
+
 #include <vector>
 
 namespace fsb {
@@ -45,22 +47,36 @@ __device__ __forceinline__ void rows_warp_sums(const float (&sq)[R], float* red,
     red[quad * 32 + lane] = keep;
 }
 
+// Every epilogue is split in two: `*_pre` issues the loads that do not depend on the GEMM result (residual rows, RoPE
+// table entries, bias, norm weights) -- it runs BEFORE the CTA waits for the other contributors' partials, so those
+// round trips overlap the wait -- and `*_apply` consumes them once the complete dot products are known.
+
 // llama.py:842-845 / 944-946: y = Linear(...) (bf16), x = x + y (bf16); plus sum_i x^2 of this tile per row
 template <int R>
-__device__ __forceinline__ void epi_resid(const StepGemmParams& p, const float (&acc)[R], int tile, int tid, int j0,
-                                          float* red) {
+struct ResidPre {
+    float xin[R];
+    float b;
+};
+template <int R>
+__device__ __forceinline__ void epi_resid_pre(const StepGemmParams& p, int tile, int tid, int j0, ResidPre<R>& q) {
+    const int i = tile * 128 + tid;
+    const bool ok = i < p.n_out;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        q.xin[r] = (p.resid != nullptr && ok && j0 + r < p.rows) ? bf2f(p.resid[static_cast<size_t>(j0 + r) * p.n_out + i]) : 0.f;
+    q.b = (p.bias != nullptr && ok) ? bf2f(p.bias[i]) : 0.f;
+}
+template <int R>
+__device__ __forceinline__ void epi_resid_apply(const StepGemmParams& p, const float (&acc)[R], const ResidPre<R>& q,
+                                                int tile, int tid, int j0, float* red) {
     const int quad = tid >> 5, lane = tid & 31;
     const int i = tile * 128 + tid;
     const bool ok = i < p.n_out;
-    float xin[R], sq[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-        xin[r] = (p.resid != nullptr && ok && j0 + r < p.rows) ? bf2f(p.resid[static_cast<size_t>(j0 + r) * p.n_out + i]) : 0.f;
-    const float b = (p.bias != nullptr && ok) ? bf2f(p.bias[i]) : 0.f;
+    float sq[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const float y = p.bias != nullptr ? rbf(acc[r] + b) : rbf(acc[r]);
-        const float x = p.resid != nullptr ? rbf(xin[r] + y) : y;
+        const float y = p.bias != nullptr ? rbf(acc[r] + q.b) : rbf(acc[r]);
+        const float x = p.resid != nullptr ? rbf(q.xin[r] + y) : y;
         const bool live = ok && j0 + r < p.rows;
         if (live) p.x_out[static_cast<size_t>(j0 + r) * p.n_out + i] = f2bf(x);
         sq[r] = live ? x * x : 0.f;
@@ -101,21 +117,46 @@ __device__ __forceinline__ void epi_logits(const StepGemmParams& p, const float 
 // llama.py:891-911: q/k/v = wqkv(x) (bf16), per-head nn.RMSNorm on q and k (fp32 math, one rounding),
 // interleaved-pair RoPE in fp32 with the bf16 table, KVCache.update (llama.py:196-214).
 template <int R>
-__device__ __forceinline__ void epi_qkv(const StepGemmParams& p, const float (&acc)[R], int tile, int tid, int j0,
-                                        float* red) {
+struct QkvPre {
+    uint32_t cs[R];  // (cos, sin) bf16 pair of this lane's rotary pair at the row's position
+    float b, wn;
+};
+template <int R>
+__device__ __forceinline__ void epi_qkv_pre(const StepGemmParams& p, int tile, int tid, int j0, QkvPre<R>& q) {
     const int quad = tid >> 5, lane = tid & 31;
     const int fb = tile * 128 + quad * 32;  // a warp's 32 features never straddle a head (Dh % 32 == 0)
     const bool wok = fb < p.n_out;
     const int head = fb / p.Dh;
     const int d = fb - head * p.Dh + lane;
     const int kind = head < p.H ? 0 : (head < p.H + p.Hkv ? 1 : 2);
-    const float b = (p.bias != nullptr && wok) ? bf2f(p.bias[fb + lane]) : 0.f;
+    const __nv_bfloat16* nw = kind == 0 ? p.q_norm : (kind == 1 ? p.k_norm : nullptr);
+    q.b = (p.bias != nullptr && wok) ? bf2f(p.bias[fb + lane]) : 0.f;
+    q.wn = (nw != nullptr && wok) ? bf2f(nw[d]) : 1.f;
+    const int half = p.Dh >> 1;
+    // (row positions are re-read in the apply step: by then they sit in L1; keeping them would cost R registers)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const bool live = wok && kind != 2 && j0 + r < p.rows;
+        const int pos = live ? p.row_pos[j0 + r] : 0;
+        q.cs[r] = live ? *reinterpret_cast<const uint32_t*>(
+                             p.freqs + (static_cast<size_t>(max(0, min(pos, p.S - 1))) * half + (d >> 1)) * 2)
+                       : 0u;
+    }
+}
+template <int R>
+__device__ __forceinline__ void epi_qkv_apply(const StepGemmParams& p, const float (&acc)[R], const QkvPre<R>& q, int tile,
+                                              int tid, int j0, float* red) {
+    const int quad = tid >> 5, lane = tid & 31;
+    const int fb = tile * 128 + quad * 32;
+    const bool wok = fb < p.n_out;
+    const int head = fb / p.Dh;
+    const int d = fb - head * p.Dh + lane;
+    const int kind = head < p.H ? 0 : (head < p.H + p.Hkv ? 1 : 2);
     float v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = p.bias != nullptr ? rbf(acc[r] + b) : rbf(acc[r]);
+    for (int r = 0; r < R; ++r) v[r] = p.bias != nullptr ? rbf(acc[r] + q.b) : rbf(acc[r]);
     if (p.q_norm != nullptr || p.k_norm != nullptr) {
-        const __nv_bfloat16* nw = kind == 0 ? p.q_norm : (kind == 1 ? p.k_norm : nullptr);
-        const bool normed = nw != nullptr && wok;
+        const bool normed = wok && (kind == 0 ? p.q_norm != nullptr : (kind == 1 && p.k_norm != nullptr));
         float sq[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) sq[r] = normed ? v[r] * v[r] : 0.f;
@@ -124,29 +165,24 @@ __device__ __forceinline__ void epi_qkv(const StepGemmParams& p, const float (&a
         if (normed) {
             const int wph = p.Dh >> 5;  // warps per head
             const int q0 = (quad / wph) * wph;
-            const float wn = bf2f(nw[d]);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 float tot = 0.f;
                 for (int u = 0; u < wph; ++u) tot += red[(q0 + u) * 32 + r];
                 const float rl = rsqrtf(tot / static_cast<float>(p.Dh) + p.qk_eps);
-                v[r] = rbf(v[r] * rl * wn);
+                v[r] = rbf(v[r] * rl * q.wn);
             }
         }
         bar_sync(1, kEpiThreads);
     }
     if (!wok) return;
-    const int half = p.Dh >> 1;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int j = j0 + r;
         if (j >= p.rows) break;
-        const int pos = p.row_pos[j];
         float o = v[r];
         if (kind != 2) {
-            const uint32_t cs = *reinterpret_cast<const uint32_t*>(
-                p.freqs + (static_cast<size_t>(min(pos, p.S - 1)) * half + (d >> 1)) * 2);
-            const float c = bf_lo(cs), s = bf_hi(cs);
+            const float c = bf_lo(q.cs[r]), s = bf_hi(q.cs[r]);
             const float partner = __shfl_xor_sync(0xffffffffu, o, 1);
             o = (lane & 1) ? __fadd_rn(__fmul_rn(o, c), __fmul_rn(partner, s))
                            : __fsub_rn(__fmul_rn(o, c), __fmul_rn(partner, s));
@@ -154,27 +190,65 @@ __device__ __forceinline__ void epi_qkv(const StepGemmParams& p, const float (&a
         }
         if (kind == 0) {
             p.q[(static_cast<size_t>(j) * p.H + head) * p.Dh + d] = f2bf(o);
-        } else if (pos < p.S) {
-            const int g = kind == 1 ? head - p.H : head - p.H - p.Hkv;
-            __nv_bfloat16* cache = kind == 1 ? p.kcache : p.vcache;
-            cache[((static_cast<size_t>(p.row_seq[j]) * p.Hkv + g) * p.S + pos) * p.Dh + d] = f2bf(o);
+        } else {
+            const int pos = p.row_pos[j];
+            if (pos >= 0 && pos < p.S) {  // a row parked at position -1 (idle slot) leaves the cache alone
+                const int g = kind == 1 ? head - p.H : head - p.H - p.Hkv;
+                __nv_bfloat16* cache = kind == 1 ? p.kcache : p.vcache;
+                cache[((static_cast<size_t>(p.row_seq[j]) * p.Hkv + g) * p.S + pos) * p.Dh + d] = f2bf(o);
+            }
         }
     }
 }
 
 template <int EPI, int R>
-__device__ __forceinline__ void run_epi(const StepGemmParams& p, const float (&acc)[R], int tile, int tid, int j0,
-                                        float* red) {
-    if (EPI == EPI_QKV) epi_qkv<R>(p, acc, tile, tid, j0, red);
-    else if (EPI == EPI_RESID) epi_resid<R>(p, acc, tile, tid, j0, red);
-    else if (EPI == EPI_SWIGLU) epi_swiglu<R>(p, acc, tile, tid, j0);
+struct EpiPre {
+    ResidPre<EPI == EPI_RESID ? R : 1> resid;
+    QkvPre<EPI == EPI_QKV ? R : 1> qkv;
+};
+template <int EPI, int R>
+__device__ __forceinline__ void epi_pre(const StepGemmParams& p, int tile, int tid, int j0, EpiPre<EPI, R>& q) {
+    if constexpr (EPI == EPI_QKV) epi_qkv_pre<R>(p, tile, tid, j0, q.qkv);
+    if constexpr (EPI == EPI_RESID) epi_resid_pre<R>(p, tile, tid, j0, q.resid);
+}
+template <int EPI, int R>
+__device__ __forceinline__ void epi_apply(const StepGemmParams& p, const float (&acc)[R], const EpiPre<EPI, R>& q, int tile,
+                                          int tid, int j0, float* red) {
+    if constexpr (EPI == EPI_QKV) epi_qkv_apply<R>(p, acc, q.qkv, tile, tid, j0, red);
+    else if constexpr (EPI == EPI_RESID) epi_resid_apply<R>(p, acc, q.resid, tile, tid, j0, red);
+    else if constexpr (EPI == EPI_SWIGLU) epi_swiglu<R>(p, acc, tile, tid, j0);
     else epi_logits<R>(p, acc, tile, tid, j0);
 }
 
-// Slot-ordered sum of all `np` partials of (tile, rows [j0, j0+R), feature tid), then the epilogue on that slice.
-// Up to 32 independent loads are in flight per thread; the additions are always in slot order.
+// One shared tile, seen from one of its `np` contributors: wait until every partial of the tile has been published,
+// then sum them IN SLOT ORDER for this CTA's slice of the batch rows [j0, j0 + R) and run the fused epilogue on it.
+// Up to 32 independent loads are in flight per thread; the order of the additions never depends on arrival order.
 template <int EPI, int R>
-__device__ __forceinline__ void fixup_slice(const StepGemmParams& p, int tile, int tid, int j0, int np, float* red) {
+__device__ __forceinline__ void finish_shared_tile(const StepGemmParams& p, int tile, int tid, int j0, int np, float* red,
+                                                   unsigned* arrive, unsigned* done, unsigned long long* trace) {
+    EpiPre<EPI, R> pre;
+    const bool mine = j0 < p.rows;  // with few live rows some contributors have no slice
+    if (mine) epi_pre<EPI, R>(p, tile, tid, j0, pre);
+    if (tid == 0) {
+        // every contributor is resident (the grid fits the GPU in one wave) and has published before it waits:
+        // bounded spin, a protocol bug becomes a trap instead of a hung GPU
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(arrive + tile) < static_cast<unsigned>(np)) {
+            if (clock64() - t0 > 4000000000ll) {
+                printf("fsb: stream-K arrival timeout block=%d tile=%d have=%u want=%d\n", blockIdx.x, tile,
+                       ld_acquire_gpu(arrive + tile), np);
+                __trap();
+            }
+        }
+        if (trace) trace[4] = globaltimer_ns();
+        // the last contributor past the wait re-arms both counters for the next launch
+        if (atomicAdd(done + tile, 1u) == static_cast<unsigned>(np - 1)) {
+            arrive[tile] = 0;
+            done[tile] = 0;
+        }
+    }
+    bar_sync(1, kEpiThreads);
+    if (!mine) return;
     constexpr int UQ = 32 / R;  // partials fetched per round
     float acc[R];
 #pragma unroll
@@ -196,7 +270,7 @@ __device__ __forceinline__ void fixup_slice(const StepGemmParams& p, int tile, i
             }
         }
     }
-    run_epi<EPI, R>(p, acc, tile, tid, j0, red);
+    epi_apply<EPI, R>(p, acc, pre, tile, tid, j0, red);
 }
 
 template <int EPI, int NORM>
@@ -224,6 +298,14 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item_begin = p.cta_items[blockIdx.x], item_end = p.cta_items[blockIdx.x + 1];
+    unsigned long long* trace = p.trace ? p.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+    if (trace && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        trace[0] = globaltimer_ns();
+        trace[6] = smid;
+        trace[7] = static_cast<unsigned long long>(item_end - item_begin);
+    }
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -274,6 +356,7 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
             pdl_wait();
+            if (trace) trace[1] = globaltimer_ns();
             int it = 0;
             for (int n = item_begin; n < item_end; ++n) {
                 const int4 w = p.sched[n];
@@ -406,6 +489,7 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t aph = static_cast<uint32_t>((n - item_begin) >> 1) & 1u;
             mbar_wait(tfull0 + 8u * a, aph);
             tc_fence_after();
+            if (trace && tid == 0 && n == item_begin) trace[2] = globaltimer_ns();
             float v[32];
             {
                 uint32_t r[32];
@@ -420,17 +504,22 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) mbar_arrive(tempty0 + 8u * a);
 
             if (p.nparts[tile] == 1) {  // the whole reduction ran in this CTA
-                run_epi<EPI, 32>(p, v, tile, tid, 0, red);
+                EpiPre<EPI, 32> pre;
+                epi_pre<EPI, 32>(p, tile, tid, 0, pre);
+                epi_apply<EPI, 32>(p, v, pre, tile, tid, 0, red);
                 continue;
             }
             float* dst = p.ws + ((static_cast<size_t>(slot) * p.tiles + tile) * 32) * 128 + tid;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
                 if (j < p.rows) __stcg(dst + j * 128, v[j]);
-            __threadfence();
             bar_sync(1, kEpiThreads);
-            if (tid == 0) atomicAdd(arrive + tile, 1u);
+            if (tid == 0) {
+                __threadfence();  // cumulative: orders the stores of all 128 threads (joined by the barrier) before the arrival
+                atomicAdd(arrive + tile, 1u);
+            }
         }
+        if (trace && tid == 0) trace[3] = globaltimer_ns();
         // Phase 2: for every shared tile, wait until all of its partials are there, then sum them IN SLOT ORDER
         // for this CTA's slice of the batch rows (contributor `slot` takes rows [slot*R, slot*R + R)) and run the
         // fused epilogue on that slice.
@@ -439,39 +528,21 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int tile = w.x, slot = w.w;
             const int np = p.nparts[tile];
             if (np == 1) continue;
-            if (tid == 0) {
-                // every contributor is resident (the grid fits the GPU in one wave) and has published before it
-                // waits: bounded spin, a protocol bug becomes a trap instead of a hung GPU
-                const long long t0 = clock64();
-                while (ld_acquire_gpu(arrive + tile) < static_cast<unsigned>(np)) {
-                    if (clock64() - t0 > 4000000000ll) {
-                        printf("fsb: stream-K arrival timeout block=%d tile=%d have=%u want=%d\n", blockIdx.x, tile,
-                               ld_acquire_gpu(arrive + tile), np);
-                        __trap();
-                    }
-                }
-                // the last contributor past the wait re-arms both counters for the next launch
-                if (atomicAdd(done + tile, 1u) == static_cast<unsigned>(np - 1)) {
-                    arrive[tile] = 0;
-                    done[tile] = 0;
-                }
-            }
-            bar_sync(1, kEpiThreads);
             int R = 1;
             while (R * np < p.rows) R <<= 1;
             const int j0 = slot * R;
-            if (j0 >= p.rows) continue;
             switch (R) {
-                case 1: fixup_slice<EPI, 1>(p, tile, tid, j0, np, red); break;
-                case 2: fixup_slice<EPI, 2>(p, tile, tid, j0, np, red); break;
-                case 4: fixup_slice<EPI, 4>(p, tile, tid, j0, np, red); break;
-                case 8: fixup_slice<EPI, 8>(p, tile, tid, j0, np, red); break;
-                default: fixup_slice<EPI, 16>(p, tile, tid, j0, np, red); break;
+                case 1: finish_shared_tile<EPI, 1>(p, tile, tid, j0, np, red, arrive, done, trace); break;
+                case 2: finish_shared_tile<EPI, 2>(p, tile, tid, j0, np, red, arrive, done, trace); break;
+                case 4: finish_shared_tile<EPI, 4>(p, tile, tid, j0, np, red, arrive, done, trace); break;
+                case 8: finish_shared_tile<EPI, 8>(p, tile, tid, j0, np, red, arrive, done, trace); break;
+                default: finish_shared_tile<EPI, 16>(p, tile, tid, j0, np, red, arrive, done, trace); break;
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (trace && threadIdx.x == 0) trace[5] = globaltimer_ns();
     if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -532,11 +603,21 @@ int step_plan_init(StepGemmPlan* plan, int epi, const __nv_bfloat16* w, int n_ou
     while (stages > 2 && 2 * (smem_of(stages) + 1024) > 228 * 1024) --stages;  // two CTAs per SM
     FSB_CHECK(stages >= 2, "step GEMM: ring too shallow");
     // The fix-up waits for the other contributors of a tile: the whole grid must be resident at once.
-    int per_sm = 0, dev = 0, sms = 0;
+    // cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for every kernel that allocates tensor memory, although
+    // two such CTAs do share an SM (verified with %smid stamps, tools/trace_step_gemms.py): count registers and
+    // shared memory ourselves.
+    int dev = 0, sms = 0, smem_sm = 0, regs_sm = 0, resv = 0;
     FSB_CUDA(cudaGetDevice(&dev));
     FSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    FSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, norm ? 256 : 192, smem_of(stages)));
-    FSB_CHECK(per_sm >= 1, "step GEMM: kernel does not fit an SM (smem %zu)", smem_of(stages));
+    FSB_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    FSB_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+    FSB_CUDA(cudaDeviceGetAttribute(&resv, cudaDevAttrReservedSharedMemoryPerBlock, dev));
+    cudaFuncAttributes fa;
+    FSB_CUDA(cudaFuncGetAttributes(&fa, kernel));
+    const int threads = norm ? 256 : 192;
+    const int regs_cta = ((fa.numRegs + 7) / 8) * 8 * threads;
+    const int per_sm = std::min<int>(regs_sm / regs_cta, smem_sm / static_cast<int>(smem_of(stages) + resv + fa.sharedSizeBytes));
+    FSB_CHECK(per_sm >= 1, "step GEMM: kernel does not fit an SM (smem %zu, %d registers)", smem_of(stages), fa.numRegs);
     if (num_ctas > per_sm * sms) num_ctas = per_sm * sms;
     // stream-K: units are (tile, k-block) pairs in tile-major order; CTA c streams units [c*U/n, (c+1)*U/n)
     const long long U = static_cast<long long>(tiles) * kblocks;

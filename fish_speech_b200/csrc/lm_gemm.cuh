@@ -65,6 +65,9 @@ struct StepGemmParams {
     // EPI_LOGITS
     float* logits;
     int logits_ld;
+    // diagnostics: optional [grid][8] globaltimer stamps {start, X may be fetched, first accumulator done, partials
+    // published, all partials of the last shared tile present, end, smid, items}
+    unsigned long long* trace;
 };
 
 struct StepGemmPlan {

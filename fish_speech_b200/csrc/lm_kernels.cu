@@ -256,7 +256,7 @@ __global__ void qkv_prep_kernel(QkvPrepArgs a) {
     }
     const int pos = a.row_pos[row];
     if (kind != 2) {
-        const __nv_bfloat16* f = a.freqs + (static_cast<size_t>(pos) * (Dh / 2) + t) * 2;
+        const __nv_bfloat16* f = a.freqs + (static_cast<size_t>(max(pos, 0)) * (Dh / 2) + t) * 2;
         const float c = bf2f(f[0]), s = bf2f(f[1]);
         const float o0 = __fsub_rn(__fmul_rn(v0, c), __fmul_rn(v1, s));
         const float o1 = __fadd_rn(__fmul_rn(v1, c), __fmul_rn(v0, s));
@@ -267,7 +267,7 @@ __global__ void qkv_prep_kernel(QkvPrepArgs a) {
     if (kind == 0) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(a.q + (static_cast<size_t>(row) * a.H + head) * Dh);
         dst[t] = packed;
-    } else if (pos < a.S) {
+    } else if (pos >= 0 && pos < a.S) {
         const int g = kind == 1 ? head - a.H : head - a.H - a.Hkv;
         __nv_bfloat16* cache = kind == 1 ? a.kcache : a.vcache;
         const int b = a.row_seq[row];
@@ -295,6 +295,11 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnArgs a, float sc
     const int row = blockIdx.y, g = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = a.row_seq[row], pos = min(a.row_pos[row], a.S - 1);  // a position past the cache reads its last row
+    if (pos < 0) {  // idle slot parked at position -1: nothing to attend to
+        for (int e = threadIdx.x; e < G * DH; e += kAttnThreads)
+            a.out[(static_cast<size_t>(row) * a.H + blockIdx.x * G) * DH + e] = f2bf(0.f);
+        return;
+    }
     const int lo = (a.window > 0 && pos - a.window + 1 > 0) ? pos - a.window + 1 : 0;
     const int L = pos - lo + 1;
     const size_t cache_base = ((static_cast<size_t>(b) * a.Hkv + g) * a.S + lo) * DH;
@@ -700,6 +705,17 @@ __global__ void frame_end_kernel(FrameEndArgs a) {
             a.pos[slot] = a.pos[slot] + 1;
     }
 }
+// 16-byte copies of one (layer, KV head) run of n_pos positions per CTA column
+__global__ void kv_copy_kernel(uint4* cache, size_t slot_stride16, size_t head_stride16, size_t layer_stride16, int src,
+                               int dst, int n16) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t base = blockIdx.z * layer_stride16 + blockIdx.y * head_stride16;
+    const uint4* s = cache + base + src * slot_stride16;
+    uint4* d = cache + base + dst * slot_stride16;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n16; e += gridDim.x * blockDim.x) d[e] = s[e];
+}
+
 __global__ void step_inc_kernel(unsigned long long* step) {
     pdl_launch_dependents();
     pdl_wait();
@@ -790,6 +806,18 @@ int launch_sample(const SampleArgs& a, cudaStream_t st) {
     FSB_CHECK(a.n > 0 && a.n <= kSampleMaxN, "sample: n=%d out of range", a.n);
     FSB_CHECK(a.ctl.state != nullptr || a.top_k >= 1, "sample: top_k must be >= 1");
     FSB_LAUNCH(sample_kernel, dim3(a.rows), dim3(kSampleThreads), 0, st, a);
+    return 0;
+}
+
+int launch_kv_copy(__nv_bfloat16* cache, int layers, int slots, int Hkv, int S, int Dh, int src, int dst, int n_pos,
+                   cudaStream_t st) {
+    if (n_pos <= 0 || src == dst) return 0;
+    FSB_CHECK(src >= 0 && src < slots && dst >= 0 && dst < slots && n_pos <= S, "kv_copy: bad slot / length");
+    FSB_CHECK(Dh % 8 == 0, "kv_copy: head_dim %d", Dh);
+    const size_t head16 = static_cast<size_t>(S) * Dh / 8, slot16 = head16 * Hkv, layer16 = slot16 * slots;
+    const int n16 = n_pos * (Dh / 8);
+    FSB_LAUNCH(kv_copy_kernel, dim3(cdiv(n16, 256 * 4), Hkv, layers), dim3(256), 0, st,
+               reinterpret_cast<uint4*>(cache), slot16, head16, layer16, src, dst, n16);
     return 0;
 }
 

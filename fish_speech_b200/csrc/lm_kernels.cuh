@@ -177,4 +177,9 @@ struct FrameEndArgs {
 };
 int launch_frame_end(const FrameEndArgs& a, cudaStream_t st);
 
+// Prefix reuse: cache[layer][dst][g][0..n_pos) = cache[layer][src][g][0..n_pos) for every layer and KV head of one
+// cache tensor laid out [layers][slots][Hkv][S][Dh].
+int launch_kv_copy(__nv_bfloat16* cache, int layers, int slots, int Hkv, int S, int Dh, int src, int dst, int n_pos,
+                   cudaStream_t st);
+
 }  // namespace fsb

@@ -143,6 +143,9 @@ class LmEngine:
         self._views = {}
         self._ctx_bound = 0  # upper bound of every slot's length, tracked on the host
         self.slot_control = False
+        self._slot_tokens: dict = {}  # slot -> token rows [C+1, T] (CPU int32) whose K/V positions [0, T) are valid
+        self.rows_reused = 0
+        self.rows_prefilled = 0
 
     def close(self):
         if getattr(self, "h", None):
@@ -260,6 +263,9 @@ class LmEngine:
         if cur:
             groups.append(cur)
         dev = self.device
+        for k, s0 in enumerate(start_pos):
+            if s0 == 0:
+                self._slot_tokens.pop(int(slots[k]), None)  # overwritten from position 0: the old record is void
         self._grow_bound(max(s0 + p.shape[1] for p, s0 in zip(prompts, start_pos)) + 1)
         with torch.cuda.device(dev):
             for grp in groups:
@@ -286,6 +292,53 @@ class LmEngine:
                     _stream()))
                 # index tensors must outlive the asynchronous kernels that read them
                 self._inflight = (d_tok, d_slot, d_pos, d_last, d_gsl)
+
+    # ---- prefix KV reuse (include/fishb200.h fsb_lm_copy_kv) -----------------------------------
+    MIN_REUSE = 16  # shorter shared prefixes are not worth a separate prefill pass
+
+    @staticmethod
+    def _common_prefix(a: torch.Tensor, b: torch.Tensor) -> int:
+        n = min(a.shape[1], b.shape[1])
+        if n == 0:
+            return 0
+        diff = (a[:, :n] != b[:, :n]).any(dim=0).nonzero()
+        return int(diff[0]) if len(diff) else n
+
+    def prefill_reusing(self, prompts: Sequence[torch.Tensor], slots: Sequence[int], sp: Optional[_lib.Sampling],
+                        do_sample: bool = True) -> list[int]:
+        """`prefill` of full prompts that skips every row whose K/V the cache already holds: the longest prefix
+        a prompt shares with what its own slot was last prefilled with, or with another slot that is not being
+        re-prefilled in this call (copied over with fsb_lm_copy_kv). The reference re-prefills the whole growing
+        conversation for every chunk of `generate_long` (inference.py:611-721); prefill is row-independent, so
+        the reused K/V is bit-identical to what a full prefill would write. Returns the reused length per prompt."""
+        host = [p.detach().to("cpu", torch.int32) for p in prompts]
+        busy = set(int(s) for s in slots)
+        reused, pieces, starts = [], [], []
+        with torch.cuda.device(self.device):
+            for p, s in zip(host, slots):
+                s = int(s)
+                best, donor = 0, s
+                for d, toks in self._slot_tokens.items():
+                    if d != s and d in busy:
+                        continue
+                    n = self._common_prefix(p, toks)
+                    if n > best:
+                        best, donor = n, d
+                best = min(best, p.shape[1] - 1)  # at least the last row is computed: its logits are sampled
+                if best < self.MIN_REUSE:
+                    best = 0
+                elif donor != s:
+                    _lib.check(self.lib.fsb_lm_copy_kv(self.h, donor, s, best, _stream()))
+                reused.append(best)
+                starts.append(best)
+            for p, b in zip(prompts, reused):
+                pieces.append(p[:, b:])
+        self.prefill(pieces, slots, sp, start_pos=starts, do_sample=do_sample)
+        for p, s in zip(host, slots):
+            self._slot_tokens[int(s)] = p
+        self.rows_reused += sum(reused)
+        self.rows_prefilled += sum(p.shape[1] - b for p, b in zip(host, reused))
+        return reused
 
     def decode(self, batch: int, nframes: int, sp: Optional[_lib.Sampling], use_graph: bool = True) -> None:
         import os

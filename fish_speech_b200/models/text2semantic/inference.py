@@ -178,7 +178,8 @@ def generate_batch(
 ) -> list[torch.Tensor]:
     """`generate` for up to 32 independent utterances at once (one KV slot each). Every sequence sees
     exactly the computation it would see alone: the kernels are batch-invariant, so the result for a
-    prompt does not depend on its batch neighbours."""
+    prompt does not depend on its batch neighbours. `reuse_prefix=True` (sampling_kwargs) prefills only the
+    rows whose K/V is not already in the cache (LmEngine.prefill_reusing): same tokens, less work."""
     if audio_parts is not None:
         raise NotImplementedError("audio_parts is not supported (nor by the reference model, llama.py:423-433)")
     cfg = model.config
@@ -204,7 +205,11 @@ def generate_batch(
     sp = eng.sampling(sampling_kwargs.get("temperature", 1.0), sampling_kwargs.get("top_p", 0.9),
                       int(sampling_kwargs.get("top_k", 30)), seed)
     eng.reset()
-    eng.prefill(list(prompts), list(range(B)), sp, do_sample=True)
+    if sampling_kwargs.get("reuse_prefix", False):
+        # keep the K/V of the rows this prompt shares with what the slot (or another slot) already holds
+        eng.prefill_reusing(list(prompts), list(range(B)), sp, do_sample=True)
+    else:
+        eng.prefill(list(prompts), list(range(B)), sp, do_sample=True)
     counts = _run_frames(eng, B, max_new_tokens, sp, first_frame_from_prefill=True)
     out_tokens = eng.buffer("out_tokens")
     outs = []
@@ -397,8 +402,10 @@ def _generate_long_plan(
             encoded = encoded.to(device=device)
             prompt_length = encoded.size(1)
             t0 = time.perf_counter()
+            # every chunk's prompt extends the previous one (the conversation only grows): reuse its K/V
             y = yield ("generate", dict(prompt=encoded, max_new_tokens=max_new_tokens, audio_masks=audio_masks,
-                                        audio_parts=audio_parts, temperature=temperature, top_p=top_p, top_k=top_k))
+                                        audio_parts=audio_parts, temperature=temperature, top_p=top_p, top_k=top_k,
+                                        reuse_prefix=True))
             t_batch = time.perf_counter() - t0
             tokens_generated = y.size(1) - prompt_length
             tokens_sec = tokens_generated / t_batch if t_batch > 0 else 0
@@ -487,7 +494,7 @@ def serve_requests(model, input_queue: "queue.Queue", max_slots: int, frames_per
                 batcher.submit(SlotRequest(
                     prompt=payload["prompt"], max_new_tokens=payload["max_new_tokens"],
                     temperature=payload["temperature"], top_p=payload["top_p"], top_k=payload["top_k"],
-                    seed=_next_seed(model),
+                    seed=_next_seed(model), reuse_prefix=bool(payload.get("reuse_prefix", False)),
                     on_done=lambda r, plan=plan, q=response_queue: advance(plan, q, r.result)))
                 waiting_queues[id(plan)] = response_queue
                 return

@@ -29,6 +29,7 @@ class SlotRequest:
     top_p: float = 0.9
     top_k: int = 30
     seed: int = 0
+    reuse_prefix: bool = False  # prefill only the rows whose K/V no slot already holds (LmEngine.prefill_reusing)
     on_done: Optional[Callable[["SlotRequest"], None]] = None
     tag: object = None
     # filled by the batcher
@@ -62,6 +63,7 @@ class ContinuousBatcher:
         self.slot_frames = 0  # sum over frames of the active slots (occupancy numerator)
         eng = self.eng
         eng.reset()
+        getattr(eng, "_slot_tokens", {}).clear()  # idle rows of the frames below write position 0 of unused slots
         eng.set_slot_control(True)
         self._state = eng.buffer("slot_state")
         self._limit = eng.buffer("slot_limit")
@@ -147,7 +149,10 @@ class ContinuousBatcher:
             self.active[r.slot] = r
             self._len[r.slot] = int(r.prompt.size(1)) + 1
         self.eng.set_context_bound_exact(max(self._len.values()) + 1)
-        self.eng.prefill([r.prompt for r in batch], slots, None, do_sample=True)
+        if any(r.reuse_prefix for r in batch) and hasattr(self.eng, "prefill_reusing"):
+            self.eng.prefill_reusing([r.prompt for r in batch], slots, None, do_sample=True)
+        else:
+            self.eng.prefill([r.prompt for r in batch], slots, None, do_sample=True)
 
     def _retire(self) -> list[SlotRequest]:
         st = torch.stack([self._state.to(torch.int32), self._n_out]).cpu()  # one small D2H copy (synchronises)
@@ -164,7 +169,8 @@ class ContinuousBatcher:
         if finished:
             idx = torch.tensor([r.slot for r in finished], dtype=torch.long, device=self._state.device)
             self._state[idx] = 0
-            self._pos[idx] = 0
+            self._pos[idx] = -1  # parked: the decode frames neither attend for this row nor touch its K/V (which a
+            #                      later request with the same prompt prefix may reuse)
         for req in finished:
             req.done.set()
             if req.on_done is not None:

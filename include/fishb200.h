@@ -122,6 +122,14 @@ int fsb_lm_prefill(fsb_lm* h, const int32_t* d_tokens, const int32_t* d_row_slot
 int fsb_lm_decode(fsb_lm* h, int batch, int nframes, const fsb_sampling* s, int use_graph,
                   void* stream);
 
+/* Prefix KV reuse (the reference re-prefills the whole growing conversation for every chunk,
+ * inference.py:611-721). The slow KV cache of a slot stays valid for the positions a prefill wrote until they are
+ * overwritten, so a prompt that shares its first p rows with what a slot already holds only needs rows [p, T):
+ * call fsb_lm_prefill with d_row_pos starting at p. fsb_lm_copy_kv makes the K/V of positions [0, n_pos) of
+ * `src_slot` available in `dst_slot` (every layer, every KV head) for requests that share a system / reference
+ * prompt with another slot. Prefill is row-independent, so reused K/V is bit-identical to recomputed K/V. */
+int fsb_lm_copy_kv(fsb_lm* h, int src_slot, int dst_slot, int n_pos, void* stream);
+
 /* Upper bound of (position + 1) over all slots for the calls that follow (prompt length + frames decoded so
  * far). Sizes the attention score buffer; must be set before prefill / decode whenever it grows. */
 int fsb_lm_set_context_bound(fsb_lm* h, int max_positions);
@@ -155,6 +163,12 @@ int fsb_lm_buffer(fsb_lm* h, const char* name, void** d_ptr, size_t* bytes);
  * the timed generation); returns the algorithmic weight bytes and launch count of one repetition. */
 int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* launches_per_rep,
                        void* stream);
+
+/* Diagnostic: the step GEMMs of the first slow layers (qkv, wo, w1|w3, w2, ...) launched back to back with per-CTA
+ * globaltimer stamps: d_trace[launch][512][8] = {start, operand fetch allowed, first accumulator complete, partials
+ * published, all partials of the last shared tile present, end, smid, items}. Returns the number of launches traced
+ * (0 = failure); overwrites the decode state like fsb_lm_bench_gemms. */
+int fsb_lm_trace_step_gemms(fsb_lm* h, unsigned long long* d_trace, int max_launches, int* grid_out, void* stream);
 
 /* Test hook for bit-exact parity of the STOCHASTIC sampler with the reference's torch RNG stream
  * (inference.py:43-46 multinomial_sample_one_no_sync, :114-144 RAS): when d_u != NULL, slot 0 takes the uniforms

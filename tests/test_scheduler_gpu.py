@@ -102,3 +102,65 @@ def test_slot_position_in_the_batch_does_not_change_a_sampled_request():
     assert all(o.done.is_set() for o in others)
     assert torch.equal(r_alone.result, r_last.result)
     assert len({tuple(o.result[0, -3:].tolist()) for o in others}) > 1  # neighbours really sampled different things
+
+
+def _grown_prompt(cfg, first: torch.Tensor, generated: torch.Tensor, extra_seed: int, extra: int) -> torch.Tensor:
+    """What generate_long does between chunks (inference.py:611-721): the next prompt = the previous prompt, the frames
+    just generated (as semantic rows: token id + codes), then new text rows."""
+    g = torch.Generator().manual_seed(extra_seed)
+    tail = torch.zeros(cfg.num_codebooks + 1, extra, dtype=first.dtype)
+    tail[0] = torch.randint(0, cfg.im_end_id, (extra,), generator=g)
+    return torch.cat([first, generated.to(first.dtype), tail], dim=1)
+
+
+def test_chunked_generation_with_prefix_reuse_equals_full_reprefill():
+    """every chunk of a long generation extends the previous prompt. With reuse_prefix the engine
+    prefills only the new rows (K/V of the old ones is still in the slot); the tokens must equal a full re-prefill."""
+    cfg = O.tiny_config()
+    w = O.make_weights(cfg, seed=91, head_gain=8.0)
+    kw = dict(temperature=0.7, top_p=0.7, top_k=1)
+    p1 = make_prompt(cfg, 91, 40)
+    reuse_model, fresh_model = build_model(cfg, w, debug=False), build_model(cfg, w, debug=False)
+    chunks_reuse, chunks_fresh, prompt = [], [], p1
+    for c in range(3):
+        a = _alone(reuse_model, prompt, 7, reuse_prefix=True, **kw)
+        b = _alone(fresh_model, prompt, 7, **kw)
+        chunks_reuse.append(a)
+        chunks_fresh.append(b)
+        assert torch.equal(a, b), f"chunk {c}: reuse != full re-prefill at {(a != b).nonzero()[:4].tolist()}"
+        prompt = _grown_prompt(cfg, prompt, a[:, prompt.size(1):], 300 + c, 9)
+    eng = reuse_model.engine
+    # chunk 0: nothing to reuse; chunks 1, 2: the whole previous prompt (40, then 40 + 7 + 9 rows)
+    assert eng.rows_reused == 40 + 56 and eng.rows_prefilled == 40 + (56 - 40) + (72 - 56)
+    # and both equal the oracle on the first chunk (the rest follows from equality above + the golden tests)
+    ref = O.generate(O.setup(cfg, w), p1, 7, noise=False, **kw)
+    assert torch.equal(chunks_fresh[0].to(torch.int32), ref.to(torch.int32))
+
+
+def test_scheduler_shares_a_prompt_prefix_across_slots():
+    """Two requests with the same 48-row system/reference prefix: the second one, admitted into another slot while the
+    first is still decoding, copies the prefix K/V (fsb_lm_copy_kv) and prefills only its own tail; both return
+    exactly what `generate` returns for them alone. A third request reuses the K/V of a RETIRED slot."""
+    from fish_speech_b200.scheduler import ContinuousBatcher, SlotRequest
+
+    cfg = O.tiny_config()
+    w = O.make_weights(cfg, seed=92, head_gain=8.0)
+    model = build_model(cfg, w, max_batch=3, debug=False)
+    shared = make_prompt(cfg, 92, 48)
+    prompts = [_grown_prompt(cfg, shared, shared[:, :0], 400 + i, 6 + 3 * i) for i in range(3)]
+    kw = dict(temperature=0.7, top_p=0.7, top_k=1)
+    alone = [_alone(model, p, 10 + 2 * i, **kw) for i, p in enumerate(prompts)]
+    eng = model.engine
+    b = ContinuousBatcher(model, max_slots=3, frames_per_poll=4)
+    eng.rows_reused = eng.rows_prefilled = 0
+    r0 = b.submit(SlotRequest(prompt=prompts[0].cuda(), max_new_tokens=10, reuse_prefix=True, **kw))
+    b.step()
+    r1 = b.submit(SlotRequest(prompt=prompts[1].cuda(), max_new_tokens=12, reuse_prefix=True, **kw))
+    b.run()
+    assert r0.slot != r1.slot and eng.rows_reused == 48
+    r2 = b.submit(SlotRequest(prompt=prompts[2].cuda(), max_new_tokens=14, reuse_prefix=True, **kw))
+    b.run()
+    b.close()
+    assert eng.rows_reused == 96 and eng.rows_prefilled == (48 + 6) + 9 + 12
+    for r, a in zip((r0, r1, r2), alone):
+        assert torch.equal(r.result.cpu(), a), (r.result.shape, a.shape)
