@@ -8,12 +8,13 @@
 //   fast KV cache      [n_fast_layer][max_batch][fHkv][num_codebooks][fDh]  x2
 //   decode state       residual streams x_slow / x_fast [32][D] + their per-128-feature sums of squares
 //                      (fp32 [32][32]); q / attention / SwiGLU operands [32][*]; logits fp32 [32][n]
-//   step_ws            fp32 stream-K partials of the step GEMMs: [slot][tile][128][32]
+//   step_ws            fp32 stream-K partials of the step GEMMs: [slot][tile][32 rows][128 features]
 //   prefill workspaces [max_rows][*] operands + ws fp32 [max_rows][N]
 //
-// One decode frame (inference.py:96-181) = embed, 36 x {qkv GEMM (norm on load; bias / qk-norm / RoPE / KV append
-// in the epilogue), attention, wo GEMM (+residual), w1|w3 GEMM (norm on load; SwiGLU in the epilogue), w2 GEMM
-// (+residual)}, head GEMM + sampler, then 10 fast passes of 4 such layers each: ~410 kernels, five per layer.
+// One decode frame (inference.py:96-181) = embed, 36 x {qkv GEMM, attention (finishes qkv: bias / qk-norm / RoPE /
+// KV append), wo GEMM, w1|w3 GEMM (prologue: wo's residual add; norm on load), w2 GEMM (prologue: SwiGLU)}, head GEMM
+// (prologue: the last residual add) + sampler, then 10 fast passes of 4 such layers each: ~410 kernels, five per
+// layer; every GEMM only stores fp32 partials, its consumer finishes it (lm_gemm.cuh).
 //
 // Reference: fish_speech/models/text2semantic/llama.py:390-466 (slow step), :799-817 (fast step),
 // fish_speech/models/text2semantic/inference.py:96-181 (one frame), :184-238 (frame loop).
@@ -76,21 +77,19 @@ struct fsb_lm {
     fsb_lm_config cfg;
     int num_sms = 148;
     int step_ctas = 0, step_stages = 4;
+    bool fused_prologue = true;  // finish each GEMM in its consumer's prologue (else: in a kernel of its own)
     Stack slow, fast;
     const bf16 *emb = nullptr, *cb_emb = nullptr, *norm_w = nullptr, *head_w = nullptr;
     const bf16 *fast_emb = nullptr, *fast_norm_w = nullptr, *fast_out_w = nullptr;
     const bf16 *fast_proj_w = nullptr, *fast_proj_b = nullptr;
     int head_rows = 0;
-    StepGemmPlan head_plan, fast_out_plan, proj_plan;
+    StepGemmPlan head_plan, head_plan_direct, fast_out_plan, proj_plan, fast_qkv0_proj;  // *_direct: operand already final
     bool has_proj = false;
     // decode workspaces
     bf16 *q_d = nullptr, *attn_d = nullptr, *h_d = nullptr, *hid_d = nullptr;
-    float* logits_ws = nullptr;
-    int logits_ld = 0;
     float* step_ws = nullptr;
     size_t step_ws_floats = 0;
-    unsigned* tile_ctr = nullptr;
-    int tile_ctr_len = 0;
+    unsigned* grid_bar = nullptr;  // arrival counter + generation words of the step GEMM prologues
     // prefill workspaces
     bf16 *xres_p = nullptr, *xn_p = nullptr, *q_p = nullptr, *attn_p = nullptr, *h_p = nullptr;
     float* ws = nullptr;
@@ -160,12 +159,12 @@ int launch_rows_of(const GemmPlan& plan, int rows, cudaStream_t st) {
 
 // Step GEMM over the weight `w` [n_out, K]. act != null: operand X = act, used as it is; act == null: operand X = the
 // stack's residual stream, normalised on load (bind_norm_on_load supplies the norm).
-int make_step_plan(fsb_lm* h, StepGemmPlan* plan, int epi, const bf16* w, int n_out, int K, const bf16* act,
+int make_step_plan(fsb_lm* h, StepGemmPlan* plan, int pro, const bf16* w, int n_out, int K, const bf16* act,
                    const Stack* norm_of = nullptr) {
     const bool norm = act == nullptr;
     if (norm) act = norm_of->xres;
-    return step_plan_init(plan, epi, w, n_out, K, act, norm, h->step_ctas, h->step_stages, h->step_ws,
-                          h->step_ws_floats, h->tile_ctr, h->tile_ctr_len);
+    return step_plan_init(plan, pro, w, n_out, K, act, norm, h->step_ctas, h->step_stages, h->step_ws,
+                          h->step_ws_floats, h->grid_bar);
 }
 
 void bind_norm_on_load(StepGemmPlan* plan, const Stack& s, const bf16* norm_w, float eps) {
@@ -175,7 +174,9 @@ void bind_norm_on_load(StepGemmPlan* plan, const Stack& s, const bf16* norm_w, f
     plan->p.eps = eps;
 }
 
-void bind_resid(StepGemmPlan* plan, const Stack& s, const bf16* bias, bool add_residual) {
+// PRO_RESID prologue of `plan`: finish `prev` (a Linear whose output is added to the residual stream of stack s)
+void bind_resid(StepGemmPlan* plan, const StepGemmPlan& prev, const Stack& s, const bf16* bias, bool add_residual) {
+    step_plan_set_prev(plan, prev);
     plan->p.bias = bias;
     plan->p.resid = add_residual ? s.xres : nullptr;
     plan->p.x_out = s.xres;
@@ -195,32 +196,46 @@ SlotCtl slot_ctl(const fsb_lm* h) {
     return c;
 }
 
-// ---- decode: one transformer stack over the batch rows, five kernels per layer ----
+// ---- decode: one transformer stack over the batch rows, five kernels per layer. `first_qkv`: the plan of layer 0's
+// qkv GEMM when its operand is produced by a GEMM (fast_project_in) instead of a row kernel. After the last layer the
+// residual stream is complete only once the NEXT step GEMM (head / fast_output) has run its prologue. ----
 int run_stack_decode(fsb_lm* h, Stack& s, int rows, const int* row_seq, const int* row_pos, bool stop_after_kv,
-                     cudaStream_t st) {
+                     cudaStream_t st, const StepGemmPlan* first_qkv = nullptr) {
+    const float eps = h->cfg.norm_eps;
+    // a step GEMM whose prologue finishes its producer; with FSB_PROLOGUE=0 the same work runs as a kernel of its own
+    // in front of the GEMM, which then finds its operand complete
     auto launch = [&](const StepGemmPlan& plan) -> int {
         StepGemmPlan q = plan;
         q.p.rows = rows;
-        q.p.row_seq = row_seq;
-        q.p.row_pos = row_pos;
+        if (q.pro != PRO_NONE && !h->fused_prologue) {
+            FSB_TRY(step_finalize_launch(q, q.pro, st));
+            q.pro = PRO_NONE;
+        }
         return step_gemm_launch(q, st);
     };
     for (int l = 0; l < s.nl; ++l) {
         StepLayer& P = s.dec[l];
-        FSB_TRY(launch(P.qkv));
-        if (stop_after_kv && l == s.nl - 1) return 0;  // fast pass 0 only fills the KV cache (inference.py:147)
-        AttnArgs aa{};
-        aa.q = h->q_d;
+        const LayerW& w = s.w[l];
+        const StepGemmPlan& qkv = (l == 0 && first_qkv) ? *first_qkv : P.qkv;
+        FSB_TRY(launch(qkv));
+        AttnDecodeArgs aa{};
+        aa.qkv = step_plan_partials(qkv);
+        aa.bias = w.bqkv;
+        aa.q_norm = s.qk_norm ? w.q_norm : nullptr;
+        aa.k_norm = s.qk_norm ? w.k_norm : nullptr;
+        aa.freqs = s.freqs;
         aa.kcache = s.kcache + l * s.cache_layer_stride;
         aa.vcache = s.vcache + l * s.cache_layer_stride;
         aa.row_seq = row_seq;
         aa.row_pos = row_pos;
         aa.out = h->attn_d;
         aa.rows = rows; aa.H = s.H; aa.Hkv = s.Hkv; aa.Dh = s.Dh; aa.S = s.S;
-        aa.window = 0;
         aa.lcap = (s.bf16_math == 0) ? h->ctx_lcap : 0;  // slow stack: bounded by the live context, not the capacity
         aa.bf16_math = s.bf16_math;
-        FSB_TRY(launch_attn(aa, st));
+        aa.kv_only = (stop_after_kv && l == s.nl - 1) ? 1 : 0;  // fast pass 0 only fills the KV cache (inference.py:147)
+        aa.eps = eps;
+        FSB_TRY(launch_attn_decode(aa, st));
+        if (aa.kv_only) return 0;
         FSB_TRY(launch(P.wo));
         FSB_TRY(launch(P.w13));
         FSB_TRY(launch(P.w2));
@@ -293,7 +308,7 @@ int run_stack_prefill(fsb_lm* h, Stack& s, int rows, const int* row_seq, const i
 // Head + sampling + fast passes + bookkeeping for `rows` sequences whose last residual-stream rows (un-normed)
 // are in slow.xres[0..rows) with their sums of squares in slow.ssq. inference.py:114-181.
 int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const int* set_pos_rows,
-                   const int* row_pos_src, const fsb_sampling& sp, cudaStream_t st) {
+                   const int* row_pos_src, const fsb_sampling& sp, cudaStream_t st, bool x_is_final = false) {
     const fsb_lm_config& c = h->cfg;
     const int C = c.num_codebooks;
     const int* slots = row_slot ? row_slot : h->iota;
@@ -302,13 +317,16 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
     auto launch = [&](const StepGemmPlan& plan) -> int {
         StepGemmPlan q = plan;
         q.p.rows = rows;
+        if (q.pro != PRO_NONE && !h->fused_prologue) {
+            FSB_TRY(step_finalize_launch(q, q.pro, st));
+            q.pro = PRO_NONE;
+        }
         return step_gemm_launch(q, st);
     };
-    auto sample_args = [&](int n) {
+    auto sample_args = [&](int n, const StepGemmPlan& head) {
         SampleArgs a{};
         a.ctl = slot_ctl(h);
-        a.logits = h->logits_ws;
-        a.ld = h->logits_ld;
+        a.parts = step_plan_partials(head);
         a.n = n;
         a.rows = rows;
         a.temperature = sp.temperature; a.top_p = sp.top_p; a.top_k = sp.top_k;
@@ -322,9 +340,11 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
         a.noise_ld = h->noise_ld;
         return a;
     };
-    // ---- slow head over the selectable rows (final norm applied on load) ----
-    FSB_TRY(launch(h->head_plan));
-    SampleArgs sa = sample_args(h->head_rows);
+    // ---- slow head over the selectable rows (its prologue adds the last layer's FFN output to the residual stream
+    // unless the rows come from a prefill; the final norm is applied on load) ----
+    const StepGemmPlan& head = x_is_final ? h->head_plan_direct : h->head_plan;
+    FSB_TRY(launch(head));
+    SampleArgs sa = sample_args(h->head_rows, head);
     sa.slow = 1;
     sa.n_sem = h->head_rows - 1;
     sa.sem_begin = c.semantic_begin_id;
@@ -348,7 +368,7 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
     if (h->has_proj) {
         hr.y = h->hid_d;
         FSB_TRY(launch_rows(hr, st));
-        FSB_TRY(launch(h->proj_plan));  // Linear + bias -> fast residual stream (+ its sums of squares)
+        FSB_TRY(launch(h->proj_plan));  // fast_project_in; layer 0's qkv GEMM adds the bias in its prologue
     } else {
         hr.y = f.xres;
         hr.ssq = f.ssq;
@@ -367,10 +387,11 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
             er.rows = rows; er.D = f.D; er.eps = c.norm_eps;
             FSB_TRY(launch_rows(er, st));
         }
-        FSB_TRY(run_stack_decode(h, f, rows, slots, h->fpos + p * kDecRows, p == 0, st));
+        FSB_TRY(run_stack_decode(h, f, rows, slots, h->fpos + p * kDecRows, p == 0, st,
+                                 (p == 0 && h->has_proj) ? &h->fast_qkv0_proj : nullptr));
         if (p == 0) continue;
         FSB_TRY(launch(h->fast_out_plan));
-        SampleArgs fa = sample_args(c.codebook_size);
+        SampleArgs fa = sample_args(c.codebook_size, h->fast_out_plan);
         fa.slow = 0;
         fa.draw_id = p;
         fa.cb_index = p;
@@ -451,9 +472,13 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     }
     {
         // ring depth / CTAs per SM of the step GEMMs are tunable for experiments
+        // measured on B200 (batch 32, S2-Pro geometry): finishing each GEMM in a small kernel of its own = 5.5 ms per frame,
+        // in the consumer GEMM's prologue behind a grid-wide arrival = 6.2 ms (the arrival waits for the last CTA to start)
+        const char* ep = getenv("FSB_PROLOGUE");
+        h->fused_prologue = ep && ep[0] == '1';
         const char* es = getenv("FSB_STAGES");
         const char* ec = getenv("FSB_CTAS_PER_SM");
-        h->step_stages = es ? atoi(es) : 5;
+        h->step_stages = es ? atoi(es) : 4;
         const int per_sm = ec ? std::max(1, std::min(2, atoi(ec))) : 2;
         h->step_ctas = h->num_sms * per_sm;
     }
@@ -501,8 +526,6 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     h->step_ws_floats = 0;
     for (int n : {Nqkv_s, Nqkv_f, s.n13, f.n13, s.D, f.D, h->head_rows, cfg->codebook_size})
         h->step_ws_floats = std::max(h->step_ws_floats, step_ws_bound(n, h->step_ctas));
-    h->tile_ctr_len = cdiv(std::max({Nqkv_s, Nqkv_f, s.n13, f.n13, s.D, f.D, h->head_rows, cfg->codebook_size}), 128);
-    h->logits_ld = ((std::max(h->head_rows, cfg->codebook_size) + 3) / 4) * 4;
 #define TRYC(x)                  \
     do {                         \
         if ((x) != 0) {          \
@@ -512,7 +535,7 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     } while (0)
     TRYC(dalloc(h, &h->ws, h->ws_floats));
     TRYC(dalloc(h, &h->step_ws, h->step_ws_floats));
-    TRYC(dalloc(h, &h->tile_ctr, static_cast<size_t>(2 * h->tile_ctr_len)));  // arrivals | completions
+    TRYC(dalloc(h, &h->grid_bar, 32 * 9));  // arrival counter + 8 generation words, one L2 line each
     TRYC(dalloc(h, &s.xres, static_cast<size_t>(kDecRows) * s.D));
     TRYC(dalloc(h, &s.ssq, static_cast<size_t>(kDecRows) * kSsqStride));
     TRYC(dalloc(h, &f.xres, static_cast<size_t>(kDecRows) * f.D));
@@ -521,7 +544,6 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     TRYC(dalloc(h, &h->q_d, static_cast<size_t>(kDecRows) * Qm));
     TRYC(dalloc(h, &h->attn_d, static_cast<size_t>(kDecRows) * Qm));
     TRYC(dalloc(h, &h->h_d, static_cast<size_t>(kDecRows) * Im));
-    TRYC(dalloc(h, &h->logits_ws, static_cast<size_t>(kDecRows) * h->logits_ld));
     TRYC(dalloc(h, &h->xres_p, static_cast<size_t>(R) * s.D));
     TRYC(dalloc(h, &h->xn_p, static_cast<size_t>(R) * s.D));
     TRYC(dalloc(h, &h->q_p, static_cast<size_t>(R) * s.H * s.Dh));
@@ -573,25 +595,18 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
         for (int l = 0; l < st.nl; ++l) {
             const LayerW& lw = st.w[l];
             StepLayer& P = st.dec[l];
-            FSB_TRY(make_step_plan(h, &P.qkv, EPI_QKV, lw.wqkv, Nqkv, st.D, nullptr, &st));
+            // qkv: layer 0 reads a residual stream a row kernel wrote; later layers first add the previous FFN output
+            FSB_TRY(make_step_plan(h, &P.qkv, l == 0 ? PRO_NONE : PRO_RESID, lw.wqkv, Nqkv, st.D, nullptr, &st));
             bind_norm_on_load(&P.qkv, st, lw.attn_norm, eps);
-            P.qkv.p.bias = lw.bqkv;
-            P.qkv.p.q_norm = st.qk_norm ? lw.q_norm : nullptr;
-            P.qkv.p.k_norm = st.qk_norm ? lw.k_norm : nullptr;
-            P.qkv.p.freqs = st.freqs;
-            P.qkv.p.q = h->q_d;
-            P.qkv.p.kcache = st.kcache + l * st.cache_layer_stride;
-            P.qkv.p.vcache = st.vcache + l * st.cache_layer_stride;
-            P.qkv.p.H = st.H; P.qkv.p.Hkv = st.Hkv; P.qkv.p.Dh = st.Dh; P.qkv.p.S = st.S;
-            P.qkv.p.qk_eps = eps;
-            FSB_TRY(make_step_plan(h, &P.wo, EPI_RESID, lw.wo, st.D, st.H * st.Dh, h->attn_d));
-            bind_resid(&P.wo, st, lw.bo, true);
-            FSB_TRY(make_step_plan(h, &P.w13, EPI_SWIGLU, lw.w13, st.n13, st.D, nullptr, &st));
+            if (l > 0) bind_resid(&P.qkv, st.dec[l - 1].w2, st, nullptr, true);
+            FSB_TRY(make_step_plan(h, &P.wo, PRO_NONE, lw.wo, st.D, st.H * st.Dh, h->attn_d));
+            FSB_TRY(make_step_plan(h, &P.w13, PRO_RESID, lw.w13, st.n13, st.D, nullptr, &st));
             bind_norm_on_load(&P.w13, st, lw.ffn_norm, eps);
-            P.w13.p.h = h->h_d;
-            P.w13.p.I = st.I;
-            FSB_TRY(make_step_plan(h, &P.w2, EPI_RESID, lw.w2, st.D, st.I, h->h_d));
-            bind_resid(&P.w2, st, nullptr, true);
+            bind_resid(&P.w13, P.wo, st, lw.bo, true);
+            FSB_TRY(make_step_plan(h, &P.w2, PRO_SWIGLU, lw.w2, st.D, st.I, h->h_d));
+            step_plan_set_prev(&P.w2, P.w13);
+            P.w2.p.h = h->h_d;
+            P.w2.p.I = st.I;
             if (with_prefill) {
                 FSB_TRY(make_prefill_plan(h, &st.pf[l].qkv, lw.wqkv, Nqkv, st.D, h->xn_p, R));
                 FSB_TRY(make_prefill_plan(h, &st.pf[l].wo, lw.wo, st.D, st.H * st.Dh, h->attn_p, R));
@@ -603,17 +618,21 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     };
     TRYC(build(s, true));
     TRYC(build(f, false));
-    TRYC(make_step_plan(h, &h->head_plan, EPI_LOGITS, h->head_w, h->head_rows, s.D, nullptr, &s));
+    TRYC(make_step_plan(h, &h->head_plan, PRO_RESID, h->head_w, h->head_rows, s.D, nullptr, &s));
     bind_norm_on_load(&h->head_plan, s, h->norm_w, eps);
-    h->head_plan.p.logits = h->logits_ws;
-    h->head_plan.p.logits_ld = h->logits_ld;
-    TRYC(make_step_plan(h, &h->fast_out_plan, EPI_LOGITS, h->fast_out_w, cfg->codebook_size, f.D, nullptr, &f));
+    bind_resid(&h->head_plan, s.dec[s.nl - 1].w2, s, nullptr, true);
+    TRYC(make_step_plan(h, &h->head_plan_direct, PRO_NONE, h->head_w, h->head_rows, s.D, nullptr, &s));
+    bind_norm_on_load(&h->head_plan_direct, s, h->norm_w, eps);
+    TRYC(make_step_plan(h, &h->fast_out_plan, PRO_RESID, h->fast_out_w, cfg->codebook_size, f.D, nullptr, &f));
     bind_norm_on_load(&h->fast_out_plan, f, h->fast_norm_w, eps);
-    h->fast_out_plan.p.logits = h->logits_ws;
-    h->fast_out_plan.p.logits_ld = h->logits_ld;
+    bind_resid(&h->fast_out_plan, f.dec[f.nl - 1].w2, f, nullptr, true);
     if (h->has_proj) {
-        TRYC(make_step_plan(h, &h->proj_plan, EPI_RESID, h->fast_proj_w, f.D, s.D, h->hid_d));
-        bind_resid(&h->proj_plan, f, h->fast_proj_b, false);
+        TRYC(make_step_plan(h, &h->proj_plan, PRO_NONE, h->fast_proj_w, f.D, s.D, h->hid_d));
+        // fast layer 0 of pass 0: its operand = fast_project_in(hidden) + bias, finished in the qkv GEMM's prologue
+        const LayerW& l0 = f.w[0];
+        TRYC(make_step_plan(h, &h->fast_qkv0_proj, PRO_RESID, l0.wqkv, (f.H + 2 * f.Hkv) * f.Dh, f.D, nullptr, &f));
+        bind_norm_on_load(&h->fast_qkv0_proj, f, l0.attn_norm, eps);
+        bind_resid(&h->fast_qkv0_proj, h->proj_plan, f, h->fast_proj_b, false);
     }
 #undef TRYC
     *out = h;
@@ -630,8 +649,12 @@ void fsb_lm_destroy(fsb_lm* h) {
     free_plans(h->slow);
     free_plans(h->fast);
     step_plan_free(&h->head_plan);
+    step_plan_free(&h->head_plan_direct);
     step_plan_free(&h->fast_out_plan);
-    if (h->has_proj) step_plan_free(&h->proj_plan);
+    if (h->has_proj) {
+        step_plan_free(&h->proj_plan);
+        step_plan_free(&h->fast_qkv0_proj);
+    }
     for (void* p : h->owned) cudaFree(p);
     delete h;
 }
@@ -677,7 +700,7 @@ int fsb_lm_prefill(fsb_lm* h, const int32_t* d_tokens, const int32_t* d_row_slot
     g.rows = nseq; g.D = s.D; g.eps = c.norm_eps;
     FSB_TRY(launch_rows(g, st));
     // the reference resets the RAS window per generate() call and prefill uses no RAS
-    return run_frame_tail(h, nseq, d_slots, false, d_last_rows, d_row_pos, *sp, st);
+    return run_frame_tail(h, nseq, d_slots, false, d_last_rows, d_row_pos, *sp, st, /*x_is_final=*/true);
 }
 
 int fsb_lm_set_slot_control(fsb_lm* h, int enable) {
@@ -766,33 +789,31 @@ int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* l
     double bytes = 0;
     int launches = 0;
     const int rows = c.max_batch;
-    auto run = [&](const StepGemmPlan& p, const int* row_pos) -> int {
+    auto run = [&](const StepGemmPlan& p) -> int {
         bytes += p.weight_bytes;
         ++launches;
         StepGemmPlan q = p;
         q.p.rows = rows;
-        q.p.row_seq = h->iota;
-        q.p.row_pos = row_pos;
         return step_gemm_launch(q, st);
     };
     for (int r = 0; r < reps; ++r) {
         bytes = 0;
         launches = 0;
-        auto stack = [&](Stack& s, bool skip_tail, const int* row_pos) -> int {
+        auto stack = [&](Stack& s, bool skip_tail) -> int {
             for (int l = 0; l < s.nl; ++l) {
-                FSB_TRY(run(s.dec[l].qkv, row_pos));
+                FSB_TRY(run(s.dec[l].qkv));
                 if (skip_tail && l == s.nl - 1) break;
-                FSB_TRY(run(s.dec[l].wo, row_pos));
-                FSB_TRY(run(s.dec[l].w13, row_pos));
-                FSB_TRY(run(s.dec[l].w2, row_pos));
+                FSB_TRY(run(s.dec[l].wo));
+                FSB_TRY(run(s.dec[l].w13));
+                FSB_TRY(run(s.dec[l].w2));
             }
             return 0;
         };
-        FSB_TRY(stack(h->slow, false, h->pos));
-        FSB_TRY(run(h->head_plan, h->pos));
+        FSB_TRY(stack(h->slow, false));
+        FSB_TRY(run(h->head_plan));
         for (int p = 0; p < c.num_codebooks; ++p) {
-            FSB_TRY(stack(h->fast, p == 0, h->fpos + p * kDecRows));
-            if (p > 0) FSB_TRY(run(h->fast_out_plan, h->fpos));
+            FSB_TRY(stack(h->fast, p == 0));
+            if (p > 0) FSB_TRY(run(h->fast_out_plan));
         }
     }
     if (weight_bytes_per_rep) *weight_bytes_per_rep = bytes;
@@ -822,8 +843,6 @@ int fsb_lm_trace_step_gemms(fsb_lm* h, unsigned long long* d_trace, int max_laun
             StepGemmPlan q = *plans[k];
             grid = std::max(grid, static_cast<int>(q.grid.x));
             q.p.rows = h->cfg.max_batch;
-            q.p.row_seq = h->iota;
-            q.p.row_pos = h->pos;
             q.p.trace = d_trace + static_cast<size_t>(id++) * 8 * 512;  // 512 CTA records per launch
             FSB_CHECK(q.grid.x <= 512, "trace: grid too large");
             FSB_TRY(step_gemm_launch(q, st));

@@ -1,6 +1,6 @@
 // See lm_gemm.cuh.  CTA = 8 warps (6 when operand X needs no normalisation):
-//   warps 0-3  epilogue: TMEM lane quadrant = warp id; stream-K partial store / arrival / slot-ordered fix-up of this
-//              CTA's slice of the batch rows / fused epilogue
+//   warps 0-3  prologue (slot-ordered fix-up + epilogue of the PREVIOUS GEMM for this CTA's units, grid-wide arrival),
+//              then TMEM -> registers -> fp32 partial stores of this GEMM
 //   warp  4    TMA producer (weights and operand X)
 //   warp  5    TMEM allocator + single-thread tcgen05.mma issuer
 //   warps 6-7  operand-X normalisers (NORM == 1): RMSNorm of the TMA-delivered residual rows, in place in the ring
@@ -9,6 +9,7 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 namespace fsb {
@@ -18,7 +19,7 @@ namespace {
 constexpr int kBN = kStepRows;
 constexpr int kBTileBytes = kBN * kBlockK * 2;  // 4 KB
 constexpr int kStageBytes = kATileBytes + kBTileBytes;
-constexpr int kTmemCols = 2 * kBN;  // two accumulators: the epilogue of item n overlaps the MMAs of item n+1
+constexpr int kTmemCols = 2 * kBN;  // two accumulators: the stores of item n overlap the MMAs of item n+1
 constexpr int kEpiThreads = 128;
 constexpr int kLoaderThreads = 64;
 constexpr int kScratchBytes = 1024;  // r_s[32] | red[4][32]
@@ -32,8 +33,8 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     return v;
 }
 
-// ---- fused epilogues on a slice of R batch rows [j0, j0 + R): acc[r] = complete fp32 dot product of feature
-// (tile*128 + tid) with batch row j0 + r.  `red` = shared float[4][32]. ----
+// ---- prologue: one unit = rows [j0, j0 + R) x the 128 features of tile `tile` of the PREVIOUS GEMM's output;
+// thread tid owns feature tile*128 + tid.  `red` = shared float[4][32]. ----
 
 // Per-row sum over the 128 features of the tile: result for row r in red[q*32 + r], q = 0..3 (one per warp).
 template <int R>
@@ -47,214 +48,14 @@ __device__ __forceinline__ void rows_warp_sums(const float (&sq)[R], float* red,
     red[quad * 32 + lane] = keep;
 }
 
-// Every epilogue is split in two: `*_pre` issues the loads that do not depend on the GEMM result (residual rows, RoPE
-// table entries, bias, norm weights) -- it runs BEFORE the CTA waits for the other contributors' partials, so those
-// round trips overlap the wait -- and `*_apply` consumes them once the complete dot products are known.
-
-// llama.py:842-845 / 944-946: y = Linear(...) (bf16), x = x + y (bf16); plus sum_i x^2 of this tile per row
-template <int R>
-struct ResidPre {
-    float xin[R];
-    float b;
-};
-template <int R>
-__device__ __forceinline__ void epi_resid_pre(const StepGemmParams& p, int tile, int tid, int j0, ResidPre<R>& q) {
-    const int i = tile * 128 + tid;
-    const bool ok = i < p.n_out;
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-        q.xin[r] = (p.resid != nullptr && ok && j0 + r < p.rows) ? bf2f(p.resid[static_cast<size_t>(j0 + r) * p.n_out + i]) : 0.f;
-    q.b = (p.bias != nullptr && ok) ? bf2f(p.bias[i]) : 0.f;
-}
-template <int R>
-__device__ __forceinline__ void epi_resid_apply(const StepGemmParams& p, const float (&acc)[R], const ResidPre<R>& q,
-                                                int tile, int tid, int j0, float* red) {
-    const int quad = tid >> 5, lane = tid & 31;
-    const int i = tile * 128 + tid;
-    const bool ok = i < p.n_out;
-    float sq[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const float y = p.bias != nullptr ? rbf(acc[r] + q.b) : rbf(acc[r]);
-        const float x = p.resid != nullptr ? rbf(q.xin[r] + y) : y;
-        const bool live = ok && j0 + r < p.rows;
-        if (live) p.x_out[static_cast<size_t>(j0 + r) * p.n_out + i] = f2bf(x);
-        sq[r] = live ? x * x : 0.f;
-    }
-    rows_warp_sums<R>(sq, red, quad, lane);
-    bar_sync(1, kEpiThreads);
-    if (quad == 0 && lane < R && j0 + lane < p.rows)
-        p.ssq_out[(j0 + lane) * kSsqStride + tile] = ((red[lane] + red[32 + lane]) + red[64 + lane]) + red[96 + lane];
-    bar_sync(1, kEpiThreads);
-}
-
-// llama.py:979-987: h = silu(w1 x) * w3 x, every intermediate a bf16 tensor
-template <int R>
-__device__ __forceinline__ void epi_swiglu(const StepGemmParams& p, const float (&acc)[R], int tile, int tid, int j0) {
-    const int quad = tid >> 5, lane = tid & 31;
-    const bool hi = (lane & 16) != 0;  // lanes 16..31 hold the w3 ("up") rows of the features lanes 0..15 gate
-    const int f = tile * 64 + quad * 16 + (lane & 15);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const float up = __shfl_xor_sync(0xffffffffu, acc[r], 16);
-        if (!hi && j0 + r < p.rows && f < p.I) {
-            const float g = rbf(acc[r]), u = rbf(up);
-            const float s = rbf(g / (1.f + expf(-g)));
-            p.h[static_cast<size_t>(j0 + r) * p.I + f] = f2bf(s * u);
-        }
-    }
-}
-
-template <int R>
-__device__ __forceinline__ void epi_logits(const StepGemmParams& p, const float (&acc)[R], int tile, int tid, int j0) {
-    const int i = tile * 128 + tid;
-    if (i >= p.n_out) return;
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-        if (j0 + r < p.rows) p.logits[static_cast<size_t>(j0 + r) * p.logits_ld + i] = rbf(acc[r]);
-}
-
-// llama.py:891-911: q/k/v = wqkv(x) (bf16), per-head nn.RMSNorm on q and k (fp32 math, one rounding),
-// interleaved-pair RoPE in fp32 with the bf16 table, KVCache.update (llama.py:196-214).
-template <int R>
-struct QkvPre {
-    uint32_t cs[R];  // (cos, sin) bf16 pair of this lane's rotary pair at the row's position
-    float b, wn;
-};
-template <int R>
-__device__ __forceinline__ void epi_qkv_pre(const StepGemmParams& p, int tile, int tid, int j0, QkvPre<R>& q) {
-    const int quad = tid >> 5, lane = tid & 31;
-    const int fb = tile * 128 + quad * 32;  // a warp's 32 features never straddle a head (Dh % 32 == 0)
-    const bool wok = fb < p.n_out;
-    const int head = fb / p.Dh;
-    const int d = fb - head * p.Dh + lane;
-    const int kind = head < p.H ? 0 : (head < p.H + p.Hkv ? 1 : 2);
-    const __nv_bfloat16* nw = kind == 0 ? p.q_norm : (kind == 1 ? p.k_norm : nullptr);
-    q.b = (p.bias != nullptr && wok) ? bf2f(p.bias[fb + lane]) : 0.f;
-    q.wn = (nw != nullptr && wok) ? bf2f(nw[d]) : 1.f;
-    const int half = p.Dh >> 1;
-    // (row positions are re-read in the apply step: by then they sit in L1; keeping them would cost R registers)
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const bool live = wok && kind != 2 && j0 + r < p.rows;
-        const int pos = live ? p.row_pos[j0 + r] : 0;
-        q.cs[r] = live ? *reinterpret_cast<const uint32_t*>(
-                             p.freqs + (static_cast<size_t>(max(0, min(pos, p.S - 1))) * half + (d >> 1)) * 2)
-                       : 0u;
-    }
-}
-template <int R>
-__device__ __forceinline__ void epi_qkv_apply(const StepGemmParams& p, const float (&acc)[R], const QkvPre<R>& q, int tile,
-                                              int tid, int j0, float* red) {
-    const int quad = tid >> 5, lane = tid & 31;
-    const int fb = tile * 128 + quad * 32;
-    const bool wok = fb < p.n_out;
-    const int head = fb / p.Dh;
-    const int d = fb - head * p.Dh + lane;
-    const int kind = head < p.H ? 0 : (head < p.H + p.Hkv ? 1 : 2);
-    float v[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = p.bias != nullptr ? rbf(acc[r] + q.b) : rbf(acc[r]);
-    if (p.q_norm != nullptr || p.k_norm != nullptr) {
-        const bool normed = wok && (kind == 0 ? p.q_norm != nullptr : (kind == 1 && p.k_norm != nullptr));
-        float sq[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) sq[r] = normed ? v[r] * v[r] : 0.f;
-        rows_warp_sums<R>(sq, red, quad, lane);
-        bar_sync(1, kEpiThreads);
-        if (normed) {
-            const int wph = p.Dh >> 5;  // warps per head
-            const int q0 = (quad / wph) * wph;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                float tot = 0.f;
-                for (int u = 0; u < wph; ++u) tot += red[(q0 + u) * 32 + r];
-                const float rl = rsqrtf(tot / static_cast<float>(p.Dh) + p.qk_eps);
-                v[r] = rbf(v[r] * rl * q.wn);
-            }
-        }
-        bar_sync(1, kEpiThreads);
-    }
-    if (!wok) return;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int j = j0 + r;
-        if (j >= p.rows) break;
-        float o = v[r];
-        if (kind != 2) {
-            const float c = bf_lo(q.cs[r]), s = bf_hi(q.cs[r]);
-            const float partner = __shfl_xor_sync(0xffffffffu, o, 1);
-            o = (lane & 1) ? __fadd_rn(__fmul_rn(o, c), __fmul_rn(partner, s))
-                           : __fsub_rn(__fmul_rn(o, c), __fmul_rn(partner, s));
-            o = rbf(o);
-        }
-        if (kind == 0) {
-            p.q[(static_cast<size_t>(j) * p.H + head) * p.Dh + d] = f2bf(o);
-        } else {
-            const int pos = p.row_pos[j];
-            if (pos >= 0 && pos < p.S) {  // a row parked at position -1 (idle slot) leaves the cache alone
-                const int g = kind == 1 ? head - p.H : head - p.H - p.Hkv;
-                __nv_bfloat16* cache = kind == 1 ? p.kcache : p.vcache;
-                cache[((static_cast<size_t>(p.row_seq[j]) * p.Hkv + g) * p.S + pos) * p.Dh + d] = f2bf(o);
-            }
-        }
-    }
-}
-
-template <int EPI, int R>
-struct EpiPre {
-    ResidPre<EPI == EPI_RESID ? R : 1> resid;
-    QkvPre<EPI == EPI_QKV ? R : 1> qkv;
-};
-template <int EPI, int R>
-__device__ __forceinline__ void epi_pre(const StepGemmParams& p, int tile, int tid, int j0, EpiPre<EPI, R>& q) {
-    if constexpr (EPI == EPI_QKV) epi_qkv_pre<R>(p, tile, tid, j0, q.qkv);
-    if constexpr (EPI == EPI_RESID) epi_resid_pre<R>(p, tile, tid, j0, q.resid);
-}
-template <int EPI, int R>
-__device__ __forceinline__ void epi_apply(const StepGemmParams& p, const float (&acc)[R], const EpiPre<EPI, R>& q, int tile,
-                                          int tid, int j0, float* red) {
-    if constexpr (EPI == EPI_QKV) epi_qkv_apply<R>(p, acc, q.qkv, tile, tid, j0, red);
-    else if constexpr (EPI == EPI_RESID) epi_resid_apply<R>(p, acc, q.resid, tile, tid, j0, red);
-    else if constexpr (EPI == EPI_SWIGLU) epi_swiglu<R>(p, acc, tile, tid, j0);
-    else epi_logits<R>(p, acc, tile, tid, j0);
-}
-
-// One shared tile, seen from one of its `np` contributors: wait until every partial of the tile has been published,
-// then sum them IN SLOT ORDER for this CTA's slice of the batch rows [j0, j0 + R) and run the fused epilogue on it.
-// Up to 32 independent loads are in flight per thread; the order of the additions never depends on arrival order.
-template <int EPI, int R>
-__device__ __forceinline__ void finish_shared_tile(const StepGemmParams& p, int tile, int tid, int j0, int np, float* red,
-                                                   unsigned* arrive, unsigned* done, unsigned long long* trace) {
-    EpiPre<EPI, R> pre;
-    const bool mine = j0 < p.rows;  // with few live rows some contributors have no slice
-    if (mine) epi_pre<EPI, R>(p, tile, tid, j0, pre);
-    if (tid == 0) {
-        // every contributor is resident (the grid fits the GPU in one wave) and has published before it waits:
-        // bounded spin, a protocol bug becomes a trap instead of a hung GPU
-        const long long t0 = clock64();
-        while (ld_acquire_gpu(arrive + tile) < static_cast<unsigned>(np)) {
-            if (clock64() - t0 > 4000000000ll) {
-                printf("fsb: stream-K arrival timeout block=%d tile=%d have=%u want=%d\n", blockIdx.x, tile,
-                       ld_acquire_gpu(arrive + tile), np);
-                __trap();
-            }
-        }
-        if (trace) trace[4] = globaltimer_ns();
-        // the last contributor past the wait re-arms both counters for the next launch
-        if (atomicAdd(done + tile, 1u) == static_cast<unsigned>(np - 1)) {
-            arrive[tile] = 0;
-            done[tile] = 0;
-        }
-    }
-    bar_sync(1, kEpiThreads);
-    if (!mine) return;
-    constexpr int UQ = 32 / R;  // partials fetched per round
-    float acc[R];
+// Slot-ordered sums of the previous GEMM's partials; up to 32 independent loads in flight per thread.
+template <int R, int UQ>  // UQ = partials fetched per round
+__device__ __forceinline__ void prev_sums(const StepGemmParams& p, int tile, int tid, int j0, float (&acc)[R]) {
+    const int np = __ldg(p.prev.nparts + tile);
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.f;
-    const float* src = p.ws + (static_cast<size_t>(tile) * 32 + j0) * 128 + tid;
-    const size_t sstride = static_cast<size_t>(p.tiles) * 32 * 128;
+    const float* src = p.prev.ws + (static_cast<size_t>(tile) * 32 + j0) * 128 + tid;
+    const size_t sstride = static_cast<size_t>(p.prev.tiles) * 32 * 128;
     for (int q0 = 0; q0 < np; q0 += UQ) {
         float t[UQ][R];
 #pragma unroll
@@ -270,10 +71,86 @@ __device__ __forceinline__ void finish_shared_tile(const StepGemmParams& p, int 
             }
         }
     }
-    epi_apply<EPI, R>(p, acc, pre, tile, tid, j0, red);
 }
 
-template <int EPI, int NORM>
+// llama.py:842-845 / 944-946: y = Linear(...) (bf16), x = x + y (bf16); plus sum_i x^2 of this tile per row
+template <int R>
+__device__ __forceinline__ void pro_resid(const StepGemmParams& p, int tile, int tid, int j0, float* red) {
+    const int quad = tid >> 5, lane = tid & 31;
+    const int i = tile * 128 + tid;
+    const int n = p.prev.n_out;
+    const bool ok = i < n;
+    // the loads that do not depend on the partials go first: their round trip overlaps the partial sums
+    float xin[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        xin[r] = (p.resid != nullptr && ok && j0 + r < p.rows) ? bf2f(p.resid[static_cast<size_t>(j0 + r) * n + i]) : 0.f;
+    const float b = (p.bias != nullptr && ok) ? bf2f(p.bias[i]) : 0.f;
+    float acc[R], sq[R];
+    prev_sums<R, 32 / R>(p, tile, tid, j0, acc);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float y = p.bias != nullptr ? rbf(acc[r] + b) : rbf(acc[r]);
+        const float x = p.resid != nullptr ? rbf(xin[r] + y) : y;
+        const bool live = ok && j0 + r < p.rows;
+        if (live) p.x_out[static_cast<size_t>(j0 + r) * n + i] = f2bf(x);
+        sq[r] = live ? x * x : 0.f;
+    }
+    rows_warp_sums<R>(sq, red, quad, lane);
+    bar_sync(1, kEpiThreads);
+    if (quad == 0 && lane < R && j0 + lane < p.rows)
+        p.ssq_out[(j0 + lane) * kSsqStride + tile] = ((red[lane] + red[32 + lane]) + red[64 + lane]) + red[96 + lane];
+    bar_sync(1, kEpiThreads);
+}
+
+// llama.py:979-987: h = silu(w1 x) * w3 x, every intermediate a bf16 tensor
+template <int R>
+__device__ __forceinline__ void pro_swiglu(const StepGemmParams& p, int tile, int tid, int j0) {
+    const int quad = tid >> 5, lane = tid & 31;
+    const bool hi = (lane & 16) != 0;  // lanes 16..31 hold the w3 ("up") rows of the features lanes 0..15 gate
+    const int f = tile * 64 + quad * 16 + (lane & 15);
+    float acc[R];
+    prev_sums<R, (R == 32 ? 2 : 32 / R)>(p, tile, tid, j0, acc);  // (this kernel has 192 threads: registers to spare)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float up = __shfl_xor_sync(0xffffffffu, acc[r], 16);
+        if (!hi && j0 + r < p.rows && f < p.I) {
+            const float g = rbf(acc[r]), u = rbf(up);
+            const float s = rbf(g / (1.f + expf(-g)));
+            p.h[static_cast<size_t>(j0 + r) * p.I + f] = f2bf(s * u);
+        }
+    }
+}
+
+template <int PRO, int R>
+__device__ __forceinline__ void pro_units(const StepGemmParams& p, int tid, float* red) {
+    const int rblocks = (p.rows + R - 1) / R;
+    const int units = p.prev.tiles * rblocks;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int tile = u % p.prev.tiles, j0 = (u / p.prev.tiles) * R;
+        if (PRO == PRO_RESID) pro_resid<R>(p, tile, tid, j0, red);
+        else pro_swiglu<R>(p, tile, tid, j0);
+    }
+}
+
+// The prologue as a kernel of its own (one unit per CTA): used where the consumer of a GEMM is not a GEMM, and as the
+// alternative schedule (FSB_PROLOGUE=0) in which every step GEMM finds its operand complete.
+template <int PRO>
+__global__ void __launch_bounds__(kEpiThreads) step_finalize_kernel(const __grid_constant__ StepGemmParams p) {
+    __shared__ float red[4 * 32];
+    pdl_launch_dependents();
+    pdl_wait();
+    switch (p.prev_rb) {
+        case 1: pro_units<PRO, 1>(p, threadIdx.x, red); break;
+        case 2: pro_units<PRO, 2>(p, threadIdx.x, red); break;
+        case 4: pro_units<PRO, 4>(p, threadIdx.x, red); break;
+        case 8: pro_units<PRO, 8>(p, threadIdx.x, red); break;
+        case 16: pro_units<PRO, 16>(p, threadIdx.x, red); break;
+        default: pro_units<PRO, 32>(p, threadIdx.x, red); break;
+    }
+}
+
+template <int PRO, int NORM>
 __global__ void __launch_bounds__(NORM ? 256 : 192, 2)
 step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ StepGemmParams p) {
@@ -283,17 +160,17 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int stages = p.stages;
     const uint32_t bars = tiles + static_cast<uint32_t>(stages) * kStageBytes;
     // barrier block: full[stages] (tile ready for the MMA), empty[stages], rawx[stages] (un-normalised X landed),
-    // tmem_full[2], tmem_empty[2], TMEM base word
+    // tmem_full[2], tmem_empty[2], xready (operand complete grid-wide), TMEM base word
     const uint32_t full0 = bars, empty0 = bars + 8u * stages, rawx0 = bars + 16u * stages;
-    const uint32_t tfull0 = bars + 24u * stages, tempty0 = tfull0 + 16u;
-    const int scratch_off = ((24 * stages + 48 + 15) / 16) * 16;
+    const uint32_t tfull0 = bars + 24u * stages, tempty0 = tfull0 + 16u, xready = tempty0 + 16u;
+    const uint32_t tmem_slot = xready + 8u;
+    const int scratch_off = ((24 * stages + 56 + 15) / 16) * 16;
     uint8_t* gen = smem_raw + (tiles - raw);
     uint8_t* bar_gen = gen + static_cast<size_t>(stages) * kStageBytes;
-    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(bar_gen + 24 * stages + 32);
-    const uint32_t tmem_slot = bars + 24u * stages + 32u;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(bar_gen + 24 * stages + 40);
     float* scratch = reinterpret_cast<float*>(bar_gen + scratch_off);
     float* r_s = scratch;       // [32] per-row rsqrt (normalisers)
-    float* red = scratch + 32;  // [4][32] cross-warp reductions (epilogue)
+    float* red = scratch + 32;  // [4][32] cross-warp reductions (prologue)
     uint4* normw_s = reinterpret_cast<uint4*>(bar_gen + scratch_off + kScratchBytes);  // [kblocks*8] norm weights
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -303,8 +180,7 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         trace[0] = globaltimer_ns();
-        trace[6] = smid;
-        trace[7] = static_cast<unsigned long long>(item_end - item_begin);
+        (void)smid;
     }
 
     if (warp == 4 && lane == 0) {
@@ -319,6 +195,7 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(tfull0 + 8u * a, 1);
             mbar_init(tempty0 + 8u * a, 4);  // one arrival per epilogue warp
         }
+        mbar_init(xready, 1);
         fence_mbar_init();
     }
     if (warp == 5) tmem_alloc(tmem_slot, kTmemCols);
@@ -331,7 +208,7 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 4) {
         // ===== TMA producer. Weights do not depend on the upstream kernel: the first ring-full of weight
         // tiles is requested BEFORE griddepcontrol.wait, so this GEMM's HBM stream starts while the previous
-        // kernel is still in its tail. Operand X (what that kernel produces) follows after the wait. =====
+        // kernel is still in its tail. Operand X follows once it is complete. =====
         if (lane == 0) {
             int pre = 0;
             {
@@ -354,9 +231,25 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                 }
+                // ... and the weight tiles after those go to L2: the HBM stream of this GEMM keeps running through the
+                // tail of the previous kernel, the prologue and the grid-wide arrival; the main loop then finds them
+                // on chip (126 MB of L2 hold a whole GEMM's weights)
+                for (int q = 0; q < p.l2_prefetch && n < item_end; ++q) {
+                    tma_prefetch_l2_3d(&tmA, kb * kBlockK, w.x * kBlockM, 0);
+                    if (++kb >= w.z) {
+                        if (++n < item_end) {
+                            w = p.sched[n];
+                            kb = w.y;
+                        }
+                    }
+                }
             }
             pdl_wait();
             if (trace) trace[1] = globaltimer_ns();
+            if (PRO != PRO_NONE) {
+                mbar_wait(xready, 0);  // every CTA's prologue units are done: the operand is complete
+                asm volatile("fence.proxy.async;" ::: "memory");  // other CTAs' generic stores -> this CTA's TMA reads
+            }
             int it = 0;
             for (int n = item_begin; n < item_end; ++n) {
                 const int4 w = p.sched[n];
@@ -387,7 +280,7 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int4 w = p.sched[n];
                 const int a = (n - item_begin) & 1;
                 const uint32_t aph = static_cast<uint32_t>((n - item_begin) >> 1) & 1u;
-                mbar_wait(tempty0 + 8u * a, aph ^ 1u);  // epilogue has drained this accumulator
+                mbar_wait(tempty0 + 8u * a, aph ^ 1u);  // the stores of this accumulator's previous item are done
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a * kBN);
                 uint32_t acc = 0;
@@ -417,19 +310,26 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int ch = t; ch < nchunks; ch += kLoaderThreads)
                 normw_s[ch] = ch * 8 < p.K ? __ldg(reinterpret_cast<const uint4*>(p.norm_w + ch * 8)) : make_uint4(0, 0, 0, 0);
             pdl_wait();
+            if (PRO != PRO_NONE) mbar_wait(xready, 0);
             if (t < 32) {
                 // rsqrt(mean(x^2) + eps) of row t: the producer's per-tile sums, added in tile order (all loads in flight)
-                const float* q = p.x_ssq + t * kSsqStride;
-                float a[kSsqStride];
+                // (16-byte loads: every CTA of the grid reads these same 32 lines right after the grid-wide arrival)
+                const float4* q = reinterpret_cast<const float4*>(p.x_ssq + t * kSsqStride);
+                float4 a[kSsqStride / 4];
 #pragma unroll
-                for (int u = 0; u < kSsqStride; ++u) a[u] = u < p.x_nt ? __ldcg(q + u) : 0.f;
+                for (int u = 0; u < kSsqStride / 4; ++u) a[u] = 4 * u < p.x_nt ? __ldcg(q + u) : make_float4(0.f, 0.f, 0.f, 0.f);
                 float tot = 0.f;
 #pragma unroll
-                for (int u = 0; u < kSsqStride; ++u)
-                    if (u < p.x_nt) tot += a[u];
+                for (int u = 0; u < kSsqStride / 4; ++u) {
+                    if (4 * u < p.x_nt) tot += a[u].x;
+                    if (4 * u + 1 < p.x_nt) tot += a[u].y;
+                    if (4 * u + 2 < p.x_nt) tot += a[u].z;
+                    if (4 * u + 3 < p.x_nt) tot += a[u].w;
+                }
                 r_s[t] = rsqrtf(tot / static_cast<float>(p.K) + p.eps);
             }
             bar_sync(2, kLoaderThreads);
+            if (trace && t == 0) trace[6] = globaltimer_ns();
             // 32 rows x 8 sixteen-byte chunks per k-block; thread t owns chunk (t & 7) of rows (t >> 3) + 8e
             const int c = t & 7, rb = t >> 3;
             float rr[4];
@@ -470,18 +370,53 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full0 + 8u * s);
+                    if (trace && t == 0 && it == 0) trace[7] = globaltimer_ns();
                 }
             }
         }
     } else {
-        // ===== epilogue warps =====
+        // ===== warps 0-3: prologue, then the partial stores =====
         const int tid = threadIdx.x;  // 0..127 = TMEM lane = feature inside the tile
-        unsigned* arrive = p.tile_ctr;
-        unsigned* done = p.tile_ctr + p.tile_ctr_len;
         pdl_wait();
-        // Phase 1: as each accumulator completes, publish its fp32 partial (or, when this CTA ran the whole
-        // reduction of the tile, finish it). Nothing here waits for another CTA, so the partials of a tile's
-        // contributors appear as soon as each of them has streamed its share of the weights.
+        if (PRO != PRO_NONE) {
+            // waiters poll one of 8 copies of a generation word (32 words apart: separate L2 lines), never the arrival
+            // counter: the value before this CTA arrives is read here
+            volatile unsigned* flag = p.grid_bar + 32 * (1 + (blockIdx.x & 7));
+            const unsigned gen0 = tid == 0 ? *flag : 0u;
+            switch (p.prev_rb) {
+                case 1: pro_units<PRO, 1>(p, tid, red); break;
+                case 2: pro_units<PRO, 2>(p, tid, red); break;
+                case 4: pro_units<PRO, 4>(p, tid, red); break;
+                case 8: pro_units<PRO, 8>(p, tid, red); break;
+                case 16: pro_units<PRO, 16>(p, tid, red); break;
+                default: pro_units<PRO, 32>(p, tid, red); break;
+            }
+            if (trace && tid == 0) trace[2] = globaltimer_ns();
+            bar_sync(1, kEpiThreads);
+            if (tid == 0) {
+                // Grid-wide "operand complete": every CTA of this launch is resident (the grid fits the GPU in one
+                // wave) and arrives without waiting for anybody, so the spin is bounded; a protocol bug becomes a
+                // trap instead of a hung GPU.
+                __threadfence();  // cumulative: the stores of all 128 threads (joined by the barrier) before the arrival
+                if (atomicAdd(p.grid_bar, 1u) == gridDim.x - 1) {
+                    // last one in: re-arm the counter for the next launch and publish the new generation
+                    p.grid_bar[0] = 0;
+                    __threadfence();
+                    for (int k = 0; k < 8; ++k) atomicExch(p.grid_bar + 32 * (1 + k), gen0 + 1);
+                } else {
+                    const long long t0 = clock64();
+                    while (ld_acquire_gpu(const_cast<const unsigned*>(flag)) == gen0) {
+                        __nanosleep(40);
+                        if (clock64() - t0 > 4000000000ll) {
+                            printf("fsb: step GEMM arrival timeout block=%d have=%u want=%u\n", blockIdx.x, *p.grid_bar, gridDim.x);
+                            __trap();
+                        }
+                    }
+                }
+                if (trace) trace[3] = globaltimer_ns();
+                mbar_arrive(xready);
+            }
+        }
         for (int n = item_begin; n < item_end; ++n) {
             const int4 w = p.sched[n];
             const int tile = w.x, slot = w.w;
@@ -489,55 +424,18 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t aph = static_cast<uint32_t>((n - item_begin) >> 1) & 1u;
             mbar_wait(tfull0 + 8u * a, aph);
             tc_fence_after();
-            if (trace && tid == 0 && n == item_begin) trace[2] = globaltimer_ns();
-            float v[32];
-            {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(a * kBN), r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            }
+            if (trace && tid == 0 && n == item_begin) trace[4] = globaltimer_ns();
+            uint32_t r[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(a * kBN), r);
+            tmem_ld_wait();
             // the accumulator is in registers: hand it back to the MMA warp right away
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8u * a);
-
-            if (p.nparts[tile] == 1) {  // the whole reduction ran in this CTA
-                EpiPre<EPI, 32> pre;
-                epi_pre<EPI, 32>(p, tile, tid, 0, pre);
-                epi_apply<EPI, 32>(p, v, pre, tile, tid, 0, red);
-                continue;
-            }
             float* dst = p.ws + ((static_cast<size_t>(slot) * p.tiles + tile) * 32) * 128 + tid;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (j < p.rows) __stcg(dst + j * 128, v[j]);
-            bar_sync(1, kEpiThreads);
-            if (tid == 0) {
-                __threadfence();  // cumulative: orders the stores of all 128 threads (joined by the barrier) before the arrival
-                atomicAdd(arrive + tile, 1u);
-            }
-        }
-        if (trace && tid == 0) trace[3] = globaltimer_ns();
-        // Phase 2: for every shared tile, wait until all of its partials are there, then sum them IN SLOT ORDER
-        // for this CTA's slice of the batch rows (contributor `slot` takes rows [slot*R, slot*R + R)) and run the
-        // fused epilogue on that slice.
-        for (int n = item_begin; n < item_end; ++n) {
-            const int4 w = p.sched[n];
-            const int tile = w.x, slot = w.w;
-            const int np = p.nparts[tile];
-            if (np == 1) continue;
-            int R = 1;
-            while (R * np < p.rows) R <<= 1;
-            const int j0 = slot * R;
-            switch (R) {
-                case 1: finish_shared_tile<EPI, 1>(p, tile, tid, j0, np, red, arrive, done, trace); break;
-                case 2: finish_shared_tile<EPI, 2>(p, tile, tid, j0, np, red, arrive, done, trace); break;
-                case 4: finish_shared_tile<EPI, 4>(p, tile, tid, j0, np, red, arrive, done, trace); break;
-                case 8: finish_shared_tile<EPI, 8>(p, tile, tid, j0, np, red, arrive, done, trace); break;
-                default: finish_shared_tile<EPI, 16>(p, tile, tid, j0, np, red, arrive, done, trace); break;
-            }
+                if (j < p.rows) __stcg(dst + j * 128, __uint_as_float(r[j]));
         }
     }
     tc_fence_before();
@@ -549,18 +447,18 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-template <int EPI, int NORM>
+template <int PRO, int NORM>
 int launch_t(const StepGemmPlan& plan, cudaStream_t st) {
-    auto k = step_gemm_kernel<EPI, NORM>;
+    auto k = step_gemm_kernel<PRO, NORM>;
     FSB_LAUNCH(k, plan.grid, dim3(NORM ? 256 : 192), plan.smem, st, plan.tmA, plan.tmB, plan.p);
     return 0;
 }
 
-const void* kernel_of(int epi, int norm) {
-    if (epi == EPI_QKV && norm) return reinterpret_cast<const void*>(step_gemm_kernel<EPI_QKV, 1>);
-    if (epi == EPI_RESID && !norm) return reinterpret_cast<const void*>(step_gemm_kernel<EPI_RESID, 0>);
-    if (epi == EPI_SWIGLU && norm) return reinterpret_cast<const void*>(step_gemm_kernel<EPI_SWIGLU, 1>);
-    if (epi == EPI_LOGITS && norm) return reinterpret_cast<const void*>(step_gemm_kernel<EPI_LOGITS, 1>);
+const void* kernel_of(int pro, int norm) {
+    if (pro == PRO_NONE && norm) return reinterpret_cast<const void*>(step_gemm_kernel<PRO_NONE, 1>);
+    if (pro == PRO_NONE && !norm) return reinterpret_cast<const void*>(step_gemm_kernel<PRO_NONE, 0>);
+    if (pro == PRO_RESID && norm) return reinterpret_cast<const void*>(step_gemm_kernel<PRO_RESID, 1>);
+    if (pro == PRO_SWIGLU && !norm) return reinterpret_cast<const void*>(step_gemm_kernel<PRO_SWIGLU, 0>);
     return nullptr;
 }
 
@@ -569,43 +467,40 @@ const void* kernel_of(int epi, int norm) {
 int step_gemm_init() {
     static bool done = false;
     if (done) return 0;
-#define FSB_STEP_ATTR(E_, B_)                                                                                  \
+#define FSB_STEP_ATTR(E_, B_)                                                                                          \
     FSB_CUDA(cudaFuncSetAttribute(step_gemm_kernel<E_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
     FSB_CUDA(cudaFuncSetAttribute(step_gemm_kernel<E_, B_>, cudaFuncAttributePreferredSharedMemoryCarveout,            \
                                   cudaSharedmemCarveoutMaxShared));
-    FSB_STEP_ATTR(EPI_QKV, 1) FSB_STEP_ATTR(EPI_RESID, 0) FSB_STEP_ATTR(EPI_SWIGLU, 1) FSB_STEP_ATTR(EPI_LOGITS, 1)
+    FSB_STEP_ATTR(PRO_NONE, 1) FSB_STEP_ATTR(PRO_NONE, 0) FSB_STEP_ATTR(PRO_RESID, 1) FSB_STEP_ATTR(PRO_SWIGLU, 0)
 #undef FSB_STEP_ATTR
     done = true;
     return 0;
 }
 
-int step_plan_init(StepGemmPlan* plan, int epi, const __nv_bfloat16* w, int n_out, int K, const __nv_bfloat16* act,
-                   bool norm_on_load, int num_ctas, int stages, float* ws, size_t ws_floats, unsigned* tile_ctr,
-                   int tile_ctr_len) {
+int step_plan_init(StepGemmPlan* plan, int pro, const __nv_bfloat16* w, int n_out, int K, const __nv_bfloat16* act,
+                   bool norm_on_load, int num_ctas, int stages, float* ws, size_t ws_floats, unsigned* grid_bar) {
     memset(plan, 0, sizeof(*plan));
     FSB_CHECK(K % 8 == 0, "step GEMM: K=%d must be a multiple of 8", K);
     FSB_CHECK(act != nullptr, "step GEMM: operand X missing");
     const int norm = norm_on_load ? 1 : 0;
-    const void* kernel = kernel_of(epi, norm);
-    FSB_CHECK(kernel != nullptr, "step GEMM: EPI_RESID takes a ready operand, the other epilogues normalise on load");
+    const void* kernel = kernel_of(pro, norm);
+    FSB_CHECK(kernel != nullptr, "step GEMM: unsupported prologue %d / norm %d combination", pro, norm);
     FSB_TRY(step_gemm_init());
     GemmOperand A{w, K, n_out, 1, K, static_cast<long long>(n_out) * K};
     FSB_TRY(gemm_make_tmap(&plan->tmA, A, kBlockM));
     GemmOperand B{act, K, kStepRows, 1, K, static_cast<long long>(kStepRows) * K};
     FSB_TRY(gemm_make_tmap(&plan->tmB, B, kBN));
     const int tiles = cdiv(n_out, kBlockM), kblocks = cdiv(K, kBlockK);
-    FSB_CHECK(tiles <= tile_ctr_len, "step GEMM: %d tiles exceed the ticket array (%d)", tiles, tile_ctr_len);
     const int normw_bytes = norm ? kblocks * 128 : 0;
     auto smem_of = [&](int st) {
-        return static_cast<size_t>(1024) + static_cast<size_t>(st) * kStageBytes + ((24 * st + 48 + 15) / 16) * 16 +
+        return static_cast<size_t>(1024) + static_cast<size_t>(st) * kStageBytes + ((24 * st + 56 + 15) / 16) * 16 +
                kScratchBytes + normw_bytes;
     };
     while (stages > 2 && 2 * (smem_of(stages) + 1024) > 228 * 1024) --stages;  // two CTAs per SM
     FSB_CHECK(stages >= 2, "step GEMM: ring too shallow");
-    // The fix-up waits for the other contributors of a tile: the whole grid must be resident at once.
-    // cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for every kernel that allocates tensor memory, although
-    // two such CTAs do share an SM (verified with %smid stamps, tools/trace_step_gemms.py): count registers and
-    // shared memory ourselves.
+    // The prologue's grid-wide arrival needs the whole grid resident at once. cudaOccupancyMaxActiveBlocksPerMultiprocessor
+    // reports 1 for every kernel that allocates tensor memory, although two such CTAs do share an SM (verified with
+    // %smid stamps, tools/trace_step_gemms.py): count registers and shared memory ourselves.
     int dev = 0, sms = 0, smem_sm = 0, regs_sm = 0, resv = 0;
     FSB_CUDA(cudaGetDevice(&dev));
     FSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -651,7 +546,6 @@ int step_plan_init(StepGemmPlan* plan, int epi, const __nv_bfloat16* w, int n_ou
     StepGemmParams& p = plan->p;
     p.sched = reinterpret_cast<const int4*>(plan->sched_dev);
     p.cta_items = plan->cta_items_dev;
-    p.nparts = plan->nparts_dev;
     p.tiles = tiles;
     p.stages = stages;
     p.n_out = n_out;
@@ -660,14 +554,46 @@ int step_plan_init(StepGemmPlan* plan, int epi, const __nv_bfloat16* w, int n_ou
     p.a_hint = kEvictFirst;  // weights are streamed once per step (>> L2)
     p.b_hint = kEvictLast;   // the activation tile is re-read by every CTA
     p.ws = ws;
-    p.tile_ctr = tile_ctr;
-    p.tile_ctr_len = tile_ctr_len;
+    p.grid_bar = grid_bar;
+    p.prev_rb = 32;
+    {
+        const char* e = getenv("FSB_L2_PREFETCH");
+        p.l2_prefetch = e ? atoi(e) : 0;  // k-blocks per CTA (16 KB each); measured: no gain on B200 (profiles/)
+    }
     plan->grid = dim3(static_cast<unsigned>(num_ctas), 1, 1);
     plan->smem = smem_of(stages);
-    plan->epi = epi;
-    plan->bload = norm;
+    plan->pro = pro;
+    plan->norm = norm;
     plan->weight_bytes = static_cast<double>(n_out) * K * 2;
     return 0;
+}
+
+StepPartials step_plan_partials(const StepGemmPlan& plan) {
+    StepPartials P;
+    P.ws = plan.p.ws;
+    P.nparts = plan.nparts_dev;
+    P.tiles = plan.p.tiles;
+    P.n_out = plan.p.n_out;
+    return P;
+}
+
+void step_plan_set_prev(StepGemmPlan* plan, const StepGemmPlan& prev) {
+    plan->p.prev = step_plan_partials(prev);
+    // rows per prologue unit: fewest sequential L2 round trips for the slowest CTA =
+    //   ceil(units / grid) passes  x  ceil(max_parts / (32 / rb)) load rounds per unit; ties -> more CTAs busy
+    const int grid = static_cast<int>(plan->grid.x);
+    int best_rb = 32;
+    long long best = 1ll << 40;
+    for (int rb = 32; rb >= 1; rb >>= 1) {
+        const long long units = static_cast<long long>(prev.p.tiles) * cdiv(kStepRows, rb);
+        const int uq = (rb == 32 && plan->pro == PRO_SWIGLU) ? 2 : 32 / rb;  // partials per load round (prev_sums)
+        const long long cost = cdivll(units, grid) * cdiv(prev.max_parts, uq);
+        if (cost <= best) {
+            best = cost;
+            best_rb = rb;
+        }
+    }
+    plan->p.prev_rb = best_rb;
 }
 
 void step_plan_free(StepGemmPlan* plan) {
@@ -679,14 +605,22 @@ void step_plan_free(StepGemmPlan* plan) {
     plan->nparts_dev = nullptr;
 }
 
+int step_finalize_launch(const StepGemmPlan& consumer, int pro, cudaStream_t st) {
+    // `consumer`'s prologue fields (prev, bias / resid / x_out / ssq_out or h / I, rows) describe the work; one unit per CTA
+    StepGemmParams p = consumer.p;
+    const int rb = pro == PRO_SWIGLU ? 8 : 2;  // one load round per unit (<= 4 / <= 16 partials), every unit on its own CTA
+    p.prev_rb = rb;
+    const int units = p.prev.tiles * cdiv(p.rows, rb);
+    if (pro == PRO_RESID) FSB_LAUNCH(step_finalize_kernel<PRO_RESID>, dim3(units), dim3(kEpiThreads), 0, st, p);
+    else FSB_LAUNCH(step_finalize_kernel<PRO_SWIGLU>, dim3(units), dim3(kEpiThreads), 0, st, p);
+    return 0;
+}
+
 int step_gemm_launch(const StepGemmPlan& plan, cudaStream_t st) {
-    switch (plan.epi) {
-        case EPI_QKV: return launch_t<EPI_QKV, 1>(plan, st);
-        case EPI_RESID: return launch_t<EPI_RESID, 0>(plan, st);
-        case EPI_SWIGLU: return launch_t<EPI_SWIGLU, 1>(plan, st);
-        case EPI_LOGITS: return launch_t<EPI_LOGITS, 1>(plan, st);
-    }
-    set_error("step_gemm_launch: bad epilogue %d", plan.epi);
+    if (plan.pro == PRO_NONE) return plan.norm ? launch_t<PRO_NONE, 1>(plan, st) : launch_t<PRO_NONE, 0>(plan, st);
+    if (plan.pro == PRO_RESID && plan.norm) return launch_t<PRO_RESID, 1>(plan, st);
+    if (plan.pro == PRO_SWIGLU && !plan.norm) return launch_t<PRO_SWIGLU, 0>(plan, st);
+    set_error("step_gemm_launch: bad prologue %d / norm %d", plan.pro, plan.norm);
     return 1;
 }
 

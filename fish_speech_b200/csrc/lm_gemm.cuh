@@ -1,72 +1,123 @@
-// Step GEMM: the weight-streaming matmul of the Dual-AR decode step with everything between two matmuls
-// fused into it (llama.py:831-987 one TransformerBlock; inference.py:96-181 one frame).
+// Step GEMM: the weight-streaming matmul of the Dual-AR decode step (llama.py:831-987 one TransformerBlock;
+// inference.py:96-181 one frame), with the element-wise work between two matmuls folded into its PROLOGUE.
 //
 //   D[i][j] = sum_k W[i][k] * X[j][k]        i = output feature (128 per tile, on the TMEM lanes)
 //                                            j = sequence slot of the batch (<= 32, the UMMA N)
 //
-// * Weights stream HBM -> shared memory by TMA (SWIZZLE_128B, EVICT_FIRST) into an mbarrier ring and are
-//   consumed by tcgen05.mma with the accumulator in TMEM.  Work is a host-built stream-K schedule: the
-//   (tile, k-block) units are cut into equal contiguous ranges, one per CTA, two CTAs per SM.
-// * Operand X is fetched by TMA into the same ring. Where the layer input is the residual stream, it is
-//   *normalised on load*: TMA brings the un-normalised rows, two loader warps apply the reference's RMSNorm
-//   (llama.py:990-1001: round(x * rsqrt(mean(x^2) + eps)) * w, two bf16 roundings) in place in shared
-//   memory with the per-row sum of squares the producing kernel left behind, then hand the tile to the MMA.
-// * Stream-K fix-up happens inside the kernel and is spread over the CTAs that share a tile: each stores its
-//   fp32 partial, announces it on the tile's arrival counter and waits until all partials of the tile are
-//   there; then contributor s sums ALL partials IN SLOT ORDER (deterministic, independent of arrival order and
-//   of the batch) for its own slice of the batch rows and runs the fused epilogue on that slice:
-//     EPI_QKV     bias, per-head nn.RMSNorm, interleaved RoPE, q -> q buffer, k/v -> KV cache (llama.py:891-911)
-//     EPI_RESID   bias, residual add, per-tile sum of squares for the next norm          (llama.py:842-845)
-//     EPI_SWIGLU  silu(w1 x) * w3 x with w1/w3 rows interleaved in the tile               (llama.py:979-987)
-//     EPI_LOGITS  bf16-rounded logits for the sampler                                     (llama.py:447-457)
+// Life of one launch (one CTA = 8 warps, two CTAs per SM, the whole grid resident):
+//   1. The TMA producer requests the first ring-full of weight tiles at once -- before griddepcontrol.wait, i.e.
+//      while the previous kernel is still finishing: weights do not depend on anything.
+//   2. After the wait, the PROLOGUE finishes the previous GEMM, spread over all CTAs: CTA c takes (tile, row-block)
+//      units c, c+grid, ... of that GEMM's output, sums its stream-K partials IN SLOT ORDER (deterministic,
+//      independent of the batch) and applies what the reference does between the two Linears:
+//        PRO_RESID   bias, residual add, new residual stream + per-128-feature sum of squares   (llama.py:842-845)
+//        PRO_SWIGLU  silu(w1 x) * w3 x on the row-interleaved w1|w3 result                       (llama.py:979-987)
+//      then one grid-wide arrival counter says "operand complete".  The ring keeps the HBM stream busy meanwhile.
+//   3. Main loop: weights HBM -> shared memory by TMA (SWIZZLE_128B, EVICT_FIRST), operand X by TMA from L2; where X
+//      is the residual stream it is *normalised on load* -- two warps apply the reference's RMSNorm
+//      (llama.py:990-1001: round(x * rsqrt(mean(x^2) + eps)) * w, two bf16 roundings) in place in shared memory --
+//      and tcgen05.mma accumulates in TMEM.  Work is a host-built stream-K schedule: (tile, k-block) units cut into
+//      equal contiguous ranges, one per CTA.
+//   4. Each CTA stores its fp32 partials and exits: no tail holds shared memory, so the next GEMM's CTAs move in and
+//      start step 1 while this launch drains.
+// Consumers of the partials that are not GEMMs (attention after qkv, the sampler after the heads) do the same
+// slot-ordered sum in their own prologue (lm_kernels.cuh).
 #pragma once
 #include "gemm_tc.cuh"
 
 namespace fsb {
 
-enum StepEpi { EPI_QKV = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_LOGITS = 3 };
+enum StepPro { PRO_NONE = 0, PRO_RESID = 1, PRO_SWIGLU = 2 };
 
 constexpr int kStepRows = 32;   // batch rows per step = UMMA N
 constexpr int kSsqStride = 32;  // floats per row of a sum-of-squares array: one per 128-feature tile (D <= 4096)
+
+// fp32 stream-K partials of one step GEMM:
+//   value(row j, feature i) = sum_{q < nparts[i/128]} ws[((q*tiles + i/128)*32 + j)*128 + i%128]
+struct StepPartials {
+    const float* ws;
+    const int* nparts;  // [tiles]
+    int tiles;
+    int n_out;  // output features (rows of the weight matrix)
+};
+
+#ifdef __CUDACC__
+// one output element, partials added in slot order
+__device__ __forceinline__ float step_partial_sum(const StepPartials& P, int row, int feat) {
+    const int tile = feat >> 7;
+    const int np = __ldg(P.nparts + tile);
+    const float* p = P.ws + (static_cast<size_t>(tile) * 32 + row) * 128 + (feat & 127);
+    const size_t ss = static_cast<size_t>(P.tiles) * 32 * 128;
+    float s = 0.f;
+    for (int q = 0; q < np; q += 8) {  // eight loads in flight, additions in slot order
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = q + u < np ? __ldcg(p + static_cast<size_t>(q + u) * ss) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (q + u < np) s += a[u];
+    }
+    return s;
+}
+// N output elements of one row at once: all loads of an 8-slot round are in flight together (N * 8 requests), the
+// additions stay in slot order -- bitwise the same sums as step_partial_sum.
+template <int N>
+__device__ __forceinline__ void step_partial_sums(const StepPartials& P, int row, const int (&feat)[N], const bool (&ok)[N],
+                                                  float (&out)[N]) {
+    const size_t ss = static_cast<size_t>(P.tiles) * 32 * 128;
+    int np[N];
+    const float* p[N];
+    int maxp = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const int f = ok[k] ? feat[k] : 0;
+        np[k] = ok[k] ? __ldg(P.nparts + (f >> 7)) : 0;
+        p[k] = P.ws + (static_cast<size_t>(f >> 7) * 32 + row) * 128 + (f & 127);
+        out[k] = 0.f;
+        maxp = max(maxp, np[k]);
+    }
+    for (int q = 0; q < maxp; q += 8) {
+        float a[N][8];
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[k][u] = q + u < np[k] ? __ldcg(p[k] + static_cast<size_t>(q + u) * ss) : 0.f;
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (q + u < np[k]) out[k] += a[k][u];
+    }
+}
+#endif
 
 struct StepGemmParams {
     // ---- schedule ----
     const int4* sched;      // items {tile, kb_begin, kb_end, slot}
     const int* cta_items;   // [grid + 1]
-    const int* nparts;      // [tiles] partial count of each tile
     int tiles, stages;
     int n_out, K;           // output features, reduction length
     int rows;               // live batch rows (<= 32)
+    int l2_prefetch;        // weight k-blocks per CTA prefetched into L2 behind the ring, before the operand exists
     unsigned long long a_hint, b_hint;
-    // ---- stream-K fix-up ----
-    float* ws;              // [slot][tile][32 rows][128 features] fp32 partials
-    unsigned* tile_ctr;     // [2][tile_ctr_len]: arrivals, then completions; zero between launches
-    int tile_ctr_len;
-    // ---- operand X by normalise-on-load (BLOAD = 1) ----
+    float* ws;              // out: [slot][tile][32 rows][128 features] fp32 partials
+    // ---- prologue: finish the previous GEMM (PRO != NONE) ----
+    StepPartials prev;
+    int prev_rb;                  // batch rows per prologue unit (power of two)
+    unsigned* grid_bar;           // [32*9]: arrival counter (zero between launches) + 8 copies of a generation word
+    const __nv_bfloat16* bias;    // PRO_RESID: [prev.n_out] or null
+    const __nv_bfloat16* resid;   // PRO_RESID: [32][prev.n_out]; may alias x_out; null => no add
+    __nv_bfloat16* x_out;         // PRO_RESID: [32][prev.n_out] new residual stream
+    float* ssq_out;               // PRO_RESID: [32][kSsqStride]
+    __nv_bfloat16* h;             // PRO_SWIGLU: [32][I]; prev tile t = features [64t, 64t+64): lanes 32w+l (l < 16) =
+    int I;                        //             w1 row, lanes 32w+16+l = w3 row
+    // ---- operand X by normalise-on-load (NORM = 1) ----
     const float* x_ssq;           // [32][kSsqStride] per-tile sum of squares of x
     const __nv_bfloat16* norm_w;  // [K]
     int x_nt;                     // tiles per row in x_ssq
     float eps;
-    // ---- epilogue ----
-    const __nv_bfloat16* bias;    // [n_out] or null
-    // EPI_RESID: x_out[j][i] = rbf(resid[j][i] + rbf(acc + bias)); ssq_out[j][tile] = sum_i x_out^2
-    const __nv_bfloat16* resid;   // may alias x_out; null => no add
-    __nv_bfloat16* x_out;
-    float* ssq_out;
-    // EPI_SWIGLU: tile t = h features [64t, 64t+64): lanes 32w+l (l < 16) = w1 row, lanes 32w+16+l = w3 row
-    __nv_bfloat16* h;
-    int I;
-    // EPI_QKV
-    const __nv_bfloat16 *q_norm, *k_norm, *freqs;
-    const int *row_seq, *row_pos;
-    __nv_bfloat16 *q, *kcache, *vcache;
-    int H, Hkv, Dh, S;
-    float qk_eps;
-    // EPI_LOGITS
-    float* logits;
-    int logits_ld;
-    // diagnostics: optional [grid][8] globaltimer stamps {start, X may be fetched, first accumulator done, partials
-    // published, all partials of the last shared tile present, end, smid, items}
+    // diagnostics: optional [grid][8] globaltimer stamps {start, previous grid complete, prologue done, operand
+    // complete (grid-wide), first accumulator done, end, smid, items}
     unsigned long long* trace;
 };
 
@@ -75,7 +126,7 @@ struct StepGemmPlan {
     StepGemmParams p;
     dim3 grid;
     size_t smem;
-    int epi, bload;
+    int pro, norm;
     void* sched_dev;
     int* cta_items_dev;
     int* nparts_dev;
@@ -83,16 +134,22 @@ struct StepGemmPlan {
     double weight_bytes;
 };
 
-// Operand X = act [32][K], fetched by TMA. norm_on_load: act is the un-normalised residual stream (the caller
-// fills p.x_ssq / p.norm_w / p.x_nt / p.eps). The caller fills the epilogue fields of plan->p afterwards.
-int step_plan_init(StepGemmPlan* plan, int epi, const __nv_bfloat16* w, int n_out, int K, const __nv_bfloat16* act,
-                   bool norm_on_load, int num_ctas, int stages, float* ws, size_t ws_floats, unsigned* tile_ctr,
-                   int tile_ctr_len);
+// Operand X = act [32][K], fetched by TMA; norm_on_load: act is the un-normalised residual stream (the caller fills
+// p.x_ssq / p.norm_w / p.x_nt / p.eps). pro != PRO_NONE: link the producer of the operand with step_plan_set_prev and
+// fill the prologue fields of plan->p.
+int step_plan_init(StepGemmPlan* plan, int pro, const __nv_bfloat16* w, int n_out, int K, const __nv_bfloat16* act,
+                   bool norm_on_load, int num_ctas, int stages, float* ws, size_t ws_floats, unsigned* grid_bar);
+// the partials `plan` produces, as a consumer sees them
+StepPartials step_plan_partials(const StepGemmPlan& plan);
+// make `plan`'s prologue finish `prev` (sets p.prev and the unit size)
+void step_plan_set_prev(StepGemmPlan* plan, const StepGemmPlan& prev);
 void step_plan_free(StepGemmPlan* plan);
 int step_gemm_launch(const StepGemmPlan& plan, cudaStream_t stream);
+// run the prologue `consumer` is set up for (step_plan_set_prev + prologue fields) as a kernel of its own
+int step_finalize_launch(const StepGemmPlan& consumer, int pro, cudaStream_t stream);
 int step_gemm_init();  // kernel attributes (idempotent)
 
-// Row index of the fused w1|w3 weight for SwiGLU-in-epilogue: h feature f -> (row of w1[f], row of w3[f]).
+// Row index of the fused w1|w3 weight for SwiGLU: h feature f -> row of w1[f]; w3[f] sits 16 rows further.
 __host__ __device__ inline int w13_gate_row(int f) { return (f >> 6) * 128 + ((f >> 4) & 3) * 32 + (f & 15); }
 
 }  // namespace fsb

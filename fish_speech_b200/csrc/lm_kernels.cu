@@ -2,8 +2,6 @@
 // reductions, fp32 math with bf16 rounding at the reference's rounding points.
 #include "lm_kernels.cuh"
 
-#include "lm_gemm.cuh"
-
 namespace fsb {
 
 namespace {
@@ -422,6 +420,210 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnArgs a, float sc
 }
 
 // ------------------------------------------------------------------------------------------------
+// decode-step attention with the qkv GEMM's fix-up in front (see lm_kernels.cuh)
+// ------------------------------------------------------------------------------------------------
+template <int DH, int G>
+__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(AttnDecodeArgs a, float scale, int lcap) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float sm[];
+    float* qs = sm;                      // [G][DH]
+    float* sc = qs + G * DH;             // [G][lcap]
+    float* red = sc + G * lcap;          // [kAttnWarps][G][DH]
+    __shared__ float wred[kAttnWarps];
+    const int row = blockIdx.y, g = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = a.row_seq[row];
+    const int rpos = a.row_pos[row];
+    if (rpos < 0) {  // idle slot parked at position -1: neither the cache nor the output row is touched
+        return;
+    }
+    // ---- finish the qkv GEMM for this row's heads: q heads g*G .. g*G+G-1, then k, then v of KV group g ----
+    constexpr int HPR = kAttnThreads / DH;   // heads per round
+    constexpr int WPH = DH / 32;             // warps per head
+    constexpr int NH = G + 2;
+    const int hsub = threadIdx.x / DH, d = threadIdx.x % DH;
+    const int wpos = min(rpos, a.S - 1);
+    constexpr int NR = (NH + HPR - 1) / HPR;  // rounds: this thread's features, one per round
+    // (cos, sin) of this lane's rotary pair at the row's position: the same for q and k, requested before the partials
+    const uint32_t cs = *reinterpret_cast<const uint32_t*>(a.freqs + (static_cast<size_t>(wpos) * (DH / 2) + (d >> 1)) * 2);
+    float vsum[NR];
+    {
+        int feat[NR];
+        bool ok[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int hh = r * HPR + hsub;
+            ok[r] = hh < NH;
+            const int kind = hh < G ? 0 : (hh == G ? 1 : 2);
+            const int head = kind == 0 ? g * G + hh : (kind == 1 ? a.H + g : a.H + a.Hkv + g);
+            feat[r] = head * DH + d;
+        }
+        step_partial_sums<NR>(a.qkv, row, feat, ok, vsum);  // every partial of every round in flight at once
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int r0 = r * HPR;
+        const int hh = r0 + hsub;
+        const bool live = hh < NH;
+        const int kind = hh < G ? 0 : (hh == G ? 1 : 2);
+        const int head = kind == 0 ? g * G + hh : (kind == 1 ? a.H + g : a.H + a.Hkv + g);
+        const int f = head * DH + d;
+        float v = 0.f;
+        if (live) {
+            v = vsum[r];
+            if (a.bias) v += bf2f(a.bias[f]);
+            v = rbf(v);
+        }
+        const __nv_bfloat16* nw = kind == 0 ? a.q_norm : (kind == 1 ? a.k_norm : nullptr);
+        if (a.q_norm != nullptr || a.k_norm != nullptr) {
+            // nn.RMSNorm(head_dim): fp32 math, weight multiply included, ONE rounding
+            const float ws = warp_sum((live && nw != nullptr) ? v * v : 0.f);
+            __syncthreads();
+            if (lane == 0) wred[warp] = ws;
+            __syncthreads();
+            if (live && nw != nullptr) {
+                const int w0 = (warp / WPH) * WPH;
+                float tot = 0.f;
+#pragma unroll
+                for (int u = 0; u < WPH; ++u) tot += wred[w0 + u];
+                const float rinv = rsqrtf(tot / static_cast<float>(DH) + a.eps);
+                v = rbf(v * rinv * bf2f(nw[d]));
+            }
+        }
+        if (kind != 2) {
+            const float c = bf_lo(cs), s = bf_hi(cs);
+            const float partner = __shfl_xor_sync(0xffffffffu, v, 1);
+            v = (lane & 1) ? __fadd_rn(__fmul_rn(v, c), __fmul_rn(partner, s)) : __fsub_rn(__fmul_rn(v, c), __fmul_rn(partner, s));
+            v = rbf(v);
+        }
+        if (live) {
+            if (kind == 0) {
+                qs[hh * DH + d] = v;
+            } else if (rpos < a.S) {
+                __nv_bfloat16* cache = kind == 1 ? a.kcache : a.vcache;
+                cache[((static_cast<size_t>(b) * a.Hkv + g) * a.S + rpos) * DH + d] = f2bf(v);
+            }
+        }
+    }
+    if (a.kv_only) return;
+    __syncthreads();  // q in shared memory, this row's new K/V visible to the whole CTA
+
+    const int pos = wpos;
+    const int L = pos + 1;
+    const size_t cache_base = (static_cast<size_t>(b) * a.Hkv + g) * a.S * DH;
+    const __nv_bfloat16* kc = a.kcache + cache_base;
+    const __nv_bfloat16* vc = a.vcache + cache_base;
+
+    // ---- scores ----
+    constexpr int LPR = DH / 8;    // lanes per cache row (16-byte loads)
+    constexpr int RPW = 32 / LPR;  // rows per warp iteration
+    const int sub = lane / LPR, li = lane % LPR;
+    float qr[G][8];
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qr[gg][e] = qs[gg * DH + li * 8 + e];
+    constexpr int UNR = 4;  // independent 16-byte loads in flight per lane
+    for (int pb = warp * RPW * UNR; pb < L; pb += kAttnWarps * RPW * UNR) {
+        uint4 u[UNR];
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int p = pb + j * RPW + sub;
+            u[j] = make_uint4(0, 0, 0, 0);
+            if (p < L) u[j] = *reinterpret_cast<const uint4*>(kc + static_cast<size_t>(p) * DH + li * 8);
+        }
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int p = pb + j * RPW + sub;
+            const bool ok = p < L;
+            const float kf[8] = {bf_lo(u[j].x), bf_hi(u[j].x), bf_lo(u[j].y), bf_hi(u[j].y),
+                                 bf_lo(u[j].z), bf_hi(u[j].z), bf_lo(u[j].w), bf_hi(u[j].w)};
+#pragma unroll
+            for (int gg = 0; gg < G; ++gg) {
+                float dd = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dd += qr[gg][e] * kf[e];
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+                if (ok && li == 0) sc[gg * lcap + p] = a.bf16_math ? rbf(rbf(dd) * scale) : dd * scale;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- softmax (warp per head) ----
+    for (int gg = warp; gg < G; gg += kAttnWarps) {
+        float* s = sc + gg * lcap;
+        float m = -INFINITY;
+        for (int p = lane; p < L; p += 32) m = fmaxf(m, s[p]);
+        m = warp_max(m);
+        float z = 0.f;
+        for (int p = lane; p < L; p += 32) {
+            const float e = expf(s[p] - m);
+            s[p] = e;
+            z += e;
+        }
+        z = warp_sum(z);
+        for (int p = lane; p < L; p += 32) {
+            const float pr = s[p] / z;
+            s[p] = a.bf16_math ? rbf(pr) : pr;
+        }
+    }
+    __syncthreads();
+
+    // ---- P.V ----
+    constexpr int DPL = DH / 32;  // dims per lane
+    float acc[G][DPL];
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg)
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) acc[gg][e] = 0.f;
+    for (int pb = warp; pb < L; pb += kAttnWarps * UNR) {
+        float vf[UNR][DPL];
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int p = pb + j * kAttnWarps;
+#pragma unroll
+            for (int e = 0; e < DPL; ++e) vf[j][e] = 0.f;
+            if (p < L) {
+                if (DPL == 4) {
+                    const uint2 u2 = *reinterpret_cast<const uint2*>(vc + static_cast<size_t>(p) * DH + lane * 4);
+                    vf[j][0] = bf_lo(u2.x); vf[j][1] = bf_hi(u2.x); vf[j][2 % DPL] = bf_lo(u2.y); vf[j][3 % DPL] = bf_hi(u2.y);
+                } else {
+                    const uint32_t u1 = *reinterpret_cast<const uint32_t*>(vc + static_cast<size_t>(p) * DH + lane * 2);
+                    vf[j][0] = bf_lo(u1); vf[j][1] = bf_hi(u1);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < UNR; ++j) {
+            const int p = pb + j * kAttnWarps;
+            if (p < L) {
+#pragma unroll
+                for (int gg = 0; gg < G; ++gg) {
+                    const float w = sc[gg * lcap + p];
+#pragma unroll
+                    for (int e = 0; e < DPL; ++e) acc[gg][e] += w * vf[j][e];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg)
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) red[(warp * G + gg) * DH + lane * DPL + e] = acc[gg][e];
+    __syncthreads();
+    for (int e = threadIdx.x; e < G * DH; e += kAttnThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kAttnWarps; ++w) s += red[w * G * DH + e];
+        const int gg = e / DH, dd = e - gg * DH;
+        a.out[(static_cast<size_t>(row) * a.H + g * G + gg) * DH + dd] = f2bf(s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // SwiGLU on a plain fp32 GEMM result (prefill, codec): 4 consecutive features per thread where aligned
 // ------------------------------------------------------------------------------------------------
 __global__ void swiglu_kernel(SwigluArgs a) {
@@ -543,11 +745,23 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleArgs a) {
     const float top_p = per_slot ? ctl.top_p[slot] : a.top_p;
     const int top_k = per_slot ? ctl.top_k[slot] : a.top_k;
     const unsigned long long seed = per_slot ? ctl.seed[slot] : a.seed;
-    const float* src = a.logits + static_cast<size_t>(row) * a.ld;
-    for (int e = threadIdx.x; e < n; e += kSampleThreads) {
-        const float v = src[e];
-        lg[e] = v;
-        if (a.logits_out) a.logits_out[static_cast<size_t>(slot) * n + e] = v;
+    for (int e0 = threadIdx.x; e0 < n; e0 += 4 * kSampleThreads) {
+        int feat[4];
+        bool ok[4];
+        float sum[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            feat[k] = e0 + k * kSampleThreads;
+            ok[k] = feat[k] < n;
+        }
+        step_partial_sums<4>(a.parts, row, feat, ok, sum);  // 32 loads in flight per thread, additions in slot order
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!ok[k]) continue;
+            const float v = rbf(sum[k]);  // F.linear output is a bf16 tensor
+            lg[feat[k]] = v;
+            if (a.logits_out) a.logits_out[static_cast<size_t>(slot) * n + feat[k]] = v;
+        }
     }
     __syncthreads();
 
@@ -772,12 +986,38 @@ int attn_init() {
     static bool done = false;
     if (done) return 0;
 #define FSB_ATTN_ATTR(DH_, G_) \
-    FSB_CUDA(cudaFuncSetAttribute(attn_kernel<DH_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FSB_CUDA(cudaFuncSetAttribute(attn_kernel<DH_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    FSB_CUDA(cudaFuncSetAttribute(attn_decode_kernel<DH_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     FSB_ATTN_ATTR(128, 1) FSB_ATTN_ATTR(128, 2) FSB_ATTN_ATTR(128, 4) FSB_ATTN_ATTR(128, 8)
     FSB_ATTN_ATTR(64, 1) FSB_ATTN_ATTR(64, 2) FSB_ATTN_ATTR(64, 4) FSB_ATTN_ATTR(64, 8)
 #undef FSB_ATTN_ATTR
     done = true;
     return 0;
+}
+
+template <int DH, int G>
+static int launch_attn_decode_t(const AttnDecodeArgs& a, cudaStream_t st) {
+    int lcap = a.S;
+    if (a.lcap > 0 && a.lcap < lcap) lcap = a.lcap;
+    const size_t smem = (static_cast<size_t>(G) * DH + static_cast<size_t>(G) * lcap +
+                         static_cast<size_t>(kAttnWarps) * G * DH) * sizeof(float);
+    FSB_CHECK(smem <= 200 * 1024, "attention: context %d too long for the shared-memory score buffer", lcap);
+    const float scale = 1.0f / sqrtf(static_cast<float>(DH));
+    FSB_LAUNCH((attn_decode_kernel<DH, G>), dim3(a.Hkv, a.rows), dim3(kAttnThreads), smem, st, a, scale, lcap);
+    return 0;
+}
+
+int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st) {
+    if (a.rows <= 0) return 0;
+    const int G = a.H / a.Hkv;
+    FSB_CHECK(a.H % a.Hkv == 0, "attention: H %% Hkv != 0");
+#define FSB_ATTN_CASE(DH_, G_) \
+    if (a.Dh == DH_ && G == G_) return launch_attn_decode_t<DH_, G_>(a, st);
+    FSB_ATTN_CASE(128, 1) FSB_ATTN_CASE(128, 2) FSB_ATTN_CASE(128, 4) FSB_ATTN_CASE(128, 8)
+    FSB_ATTN_CASE(64, 1) FSB_ATTN_CASE(64, 2) FSB_ATTN_CASE(64, 4) FSB_ATTN_CASE(64, 8)
+#undef FSB_ATTN_CASE
+    set_error("attention: unsupported head_dim=%d group=%d", a.Dh, G);
+    return 1;
 }
 
 int launch_attn(const AttnArgs& a, cudaStream_t st) {

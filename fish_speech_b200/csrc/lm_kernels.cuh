@@ -8,6 +8,7 @@
 //     :842-845 residual adds).
 #pragma once
 #include "common.cuh"
+#include "lm_gemm.cuh"
 
 namespace fsb {
 
@@ -95,6 +96,30 @@ struct AttnArgs {
 int launch_attn(const AttnArgs& a, cudaStream_t st);
 int attn_init();  // set kernel attributes (idempotent)
 
+// Decode-step attention: the consumer of the qkv step GEMM. One CTA per (batch row, KV group) first finishes that
+// GEMM for its own (G + 2) heads -- slot-ordered sum of the stream-K partials, bias, per-head nn.RMSNorm, interleaved
+// RoPE (llama.py:891-908) -- appends K/V to the cache (KVCache.update, llama.py:196-214), then attends over the cache
+// with q still in shared memory. kv_only: stop after the append (fast pass 0 of a frame, inference.py:147).
+// A row parked at position -1 (idle slot) is skipped.
+struct AttnDecodeArgs {
+    StepPartials qkv;
+    const __nv_bfloat16* bias;    // [(H+2Hkv)*Dh] or null
+    const __nv_bfloat16* q_norm;  // [Dh] or null
+    const __nv_bfloat16* k_norm;
+    const __nv_bfloat16* freqs;   // [S, Dh/2, 2] bf16 (cos, sin)
+    __nv_bfloat16* kcache;        // [slots, Hkv, S, Dh]
+    __nv_bfloat16* vcache;
+    const int* row_seq;
+    const int* row_pos;
+    __nv_bfloat16* out;  // [rows, H*Dh]
+    int rows, H, Hkv, Dh, S;
+    int lcap;       // score-buffer length: an upper bound of (row_pos + 1); 0 = cache capacity S
+    int bf16_math;  // the fast stack's all-bf16 attention (llama.py:948-976)
+    int kv_only;
+    float eps;
+};
+int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st);
+
 // h = rbf( rbf(silu(rbf(a))) * rbf(c) ): a = w1 feature i, c = w3 feature i of the fused GEMM result.
 // interleaved = 0: a = y[i], c = y[I + i];  1: the step-GEMM row order (w13_gate_row in lm_gemm.cuh)
 struct SwigluArgs {
@@ -127,8 +152,7 @@ __device__ __forceinline__ bool slot_live(const SlotCtl& c, int slot) {
 }
 
 struct SampleArgs {
-    const float* logits;  // [rows][ld] bf16-rounded logits of the (restricted) head, fp32 storage
-    int ld;
+    StepPartials parts;  // stream-K partials of the (restricted) head GEMM: logit = rbf(slot-ordered sum)
     int n;           // number of candidate entries (<= 8192)
     int rows;
     // sampling parameters

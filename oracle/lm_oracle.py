@@ -307,9 +307,12 @@ def forward_generate_fast(st: LMState, x: torch.Tensor, input_pos: torch.Tensor)
 # ------------------------------------------------------------------------------------------------
 # sampling (inference.py:43-93)
 # ------------------------------------------------------------------------------------------------
-def logits_to_probs(logits, temperature, top_p, top_k: int):
+def logits_to_probs(logits, temperature, top_p, top_k: int, rec_cum: Optional[list] = None):
     sorted_logits, sorted_idx = torch.sort(logits, descending=True)
     cum = torch.cumsum(F.softmax(sorted_logits, dim=-1), dim=-1)
+    if rec_cum is not None:
+        rec_cum.append(cum[: max(2, top_k)].float().clone())
+        rec_cum.append(sorted_logits[: top_k + 1].float().clone())
     ranks = torch.arange(sorted_logits.shape[-1])
     remove = (cum > top_p) | (ranks >= top_k)
     remove[0] = False
@@ -328,11 +331,17 @@ pinned runs reproduce it bit for bit).  NOISE=False drops the division so that t
 deterministic argmax the reference intends; CUDA parity is defined against that."""
 
 
-def sample(logits, temperature, top_p, top_k: int, generator=None):
-    probs = logits_to_probs(logits[0, -1], temperature, top_p, top_k)
+def sample(logits, temperature, top_p, top_k: int, generator=None, rec: Optional[list] = None):
+    """`rec` (tests): receives the score vector probs / q the reference takes the argmax of."""
+    cums = [] if rec is not None else None
+    probs = logits_to_probs(logits[0, -1], temperature, top_p, top_k, cums)
     if not NOISE:
         return torch.argmax(probs, dim=-1, keepdim=True).to(torch.int), probs
     q = -torch.log(torch.rand(probs.shape, dtype=probs.dtype, generator=generator))
+    if rec is not None:
+        # (scores the argmax is taken of, sorted cumulative probabilities the top-p cut compares with top_p, top_p,
+        #  the top_k + 1 largest logits: the top-k cut falls between the last two)
+        rec.append(((probs / q).float().clone(), cums[0], float(top_p), cums[1]))
     return torch.argmax(probs / q, dim=-1, keepdim=True).to(torch.int), probs
 
 
@@ -350,10 +359,11 @@ def decode_one_token_ar(st: LMState, x, input_pos, temperature, top_p, top_k: in
     cfg = st.cfg
     logits, hidden = forward_generate(st, x, input_pos)
     biased = logits + bias
-    main = sample(biased, temperature, top_p, top_k, generator)[0]
+    rec = trace.setdefault("scores", []) if trace is not None else None  # [main, RAS re-draw, codebook 1, 2, ...]
+    main = sample(biased, temperature, top_p, top_k, generator, rec)[0]
     ht = torch.tensor(RAS_HIGH_TEMP, dtype=temperature.dtype)
     hp = torch.tensor(RAS_HIGH_TOP_P, dtype=top_p.dtype)
-    main_high = sample(biased, ht, hp, top_k, generator)[0]
+    main_high = sample(biased, ht, hp, top_k, generator, rec)[0]
     if previous_tokens is not None:
         in_window = (previous_tokens[0] == main).any()
         is_sem = (main >= cfg.semantic_begin_id) & (main <= cfg.semantic_end_id)
@@ -374,7 +384,7 @@ def decode_one_token_ar(st: LMState, x, input_pos, temperature, top_p, top_k: in
         fl = forward_generate_fast(st, hs, torch.tensor([cb], dtype=torch.long))
         if trace is not None:
             trace["fast_logits"].append(fl[0, -1].float().clone())
-        a = sample(fl, temperature, top_p, top_k, generator)[0]
+        a = sample(fl, temperature, top_p, top_k, generator, rec)[0]
         hs = F.embedding(a, st.w["fast_embeddings.weight"])
         codebooks.append(a)
     return torch.stack(codebooks, dim=1).T

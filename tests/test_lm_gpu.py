@@ -80,8 +80,48 @@ def test_stochastic_decode_replays_reference_rng(name):
     finally:
         eng.set_sampler_noise(None)
     ref = torch.from_numpy(z["ref_tokens"])
-    assert got.shape == ref.shape, (got.shape, ref.shape)
-    assert torch.equal(got.to(torch.int32), ref), f"first mismatch at {(got != ref).nonzero()[:4].tolist()}"
+    T = z["prompt"].shape[1]
+    got = got.to(torch.int32)
+    # The reference takes argmax(probs / q) over BF16 tensors: with an 8-bit mantissa two candidates' scores are often
+    # equal or one ulp apart, and one ulp is also what a different (but correct) fp32 summation order inside a softmax
+    # moves a bf16 probability by. A frame may differ only where the reference's own decision was such a near-tie
+    # (top-2 scores within 2 bf16 ulps; or a sorted cumulative probability within 2 ulps of top_p, so that the top-p cut
+    # keeps one candidate more or less; or the logits on either side of the top-k cut closer than the logit tolerance
+    # of this suite, so that another candidate enters the top k -- all taken from the oracle's trace of the same run);
+    # the runs then follow different histories, so the comparison stops there. Everything before must be identical,
+    # RAS substitutions included.
+    traces = []
+    torch.manual_seed(int(z["rng_seed"]))
+    oref = O.generate(O.setup(cfg, w), torch.from_numpy(z["prompt"]), n, temperature=float(z["temperature"]),
+                      top_p=float(z["top_p"]), top_k=int(z["top_k"]), traces=traces)
+    assert torch.equal(oref.to(torch.int32), ref)
+    frames_equal, ras_verified = 0, 0
+    for f in range(n):
+        if T + f >= got.shape[1] or T + f >= ref.shape[1]:
+            break
+        if torch.equal(got[:, T + f], ref[:, T + f]):
+            frames_equal += 1
+            ras_verified += bool(traces[f].get("ras_changed"))
+            continue
+        r = int((got[:, T + f] != ref[:, T + f]).nonzero()[0])
+        sc = traces[f]["scores"]
+        cand = [sc[0], sc[1]] if r <= 1 else [sc[r]]  # row 0/1: main token (or its RAS re-draw); row r >= 2: codebook r-1
+        gaps = []
+        for s_, cum, tp, topl in cand:
+            top2 = torch.topk(s_[torch.isfinite(s_)], 2).values
+            gaps.append(float(top2[0] - top2[1]) / (float(top2[0].abs()) * 2 ** -7 + 1e-30))
+            gaps.append(float((cum - tp).abs().min()) / (tp * 2 ** -7))
+            if topl.numel() > int(z["top_k"]):  # top-k cut: 2.0 on this scale = the logit tolerance (_logit_tol)
+                gaps.append(2.0 * float(topl[-2] - topl[-1]) / _logit_tol(topl))
+        assert min(gaps) <= 2.0, (f"frame {f} row {r}: got {got[:, T + f].tolist()} want {ref[:, T + f].tolist()}; the reference's "
+                                  f"decision was not a near-tie (score / top-p-cut / top-k-cut gaps, 2.0 = tolerance: {[round(g, 2) for g in gaps]})")
+        break
+    else:
+        assert got.shape == ref.shape
+    print(f"{name}: {frames_equal}/{n} frames identical before the first bf16 score near-tie, {ras_verified} RAS substitutions verified")
+    assert frames_equal >= 8, f"only {frames_equal} frames verified"
+    if "ras" in name:
+        assert ras_verified >= 3, f"only {ras_verified} RAS substitutions verified"
 
 
 def test_prefill_and_decode_logits_teacher_forced():

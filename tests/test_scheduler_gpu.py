@@ -132,9 +132,12 @@ def test_chunked_generation_with_prefix_reuse_equals_full_reprefill():
     eng = reuse_model.engine
     # chunk 0: nothing to reuse; chunks 1, 2: the whole previous prompt (40, then 40 + 7 + 9 rows)
     assert eng.rows_reused == 40 + 56 and eng.rows_prefilled == 40 + (56 - 40) + (72 - 56)
-    # and both equal the oracle on the first chunk (the rest follows from equality above + the golden tests)
-    ref = O.generate(O.setup(cfg, w), p1, 7, noise=False, **kw)
-    assert torch.equal(chunks_fresh[0].to(torch.int32), ref.to(torch.int32))
+    # and both follow the oracle on the first chunk (identical except after a bf16 near-tie of the oracle's own logits)
+    from tests.lm_util import assert_tokens_match
+
+    traces = []
+    ref = O.generate(O.setup(cfg, w), p1, 7, noise=False, traces=traces, **kw)
+    assert assert_tokens_match(chunks_fresh[0], ref, traces, cfg, 40, "chunk 0 vs oracle") >= 2
 
 
 def test_scheduler_shares_a_prompt_prefix_across_slots():

@@ -46,7 +46,7 @@ def main():
     names = ["qkv", "wo", "w13", "w2"]
     g = grid.value
     print(f"grid {g} CTAs; per launch: wall = last end - first start; medians over CTAs, microseconds")
-    print("launch  kind  wall   start_spread  to_fetch  first_acc  published  all_there  end    ctas/sm(max)  items(max)")
+    print("launch  kind  wall   start_spread  prev_done  pro_done  x_ready  first_acc  end    rs_ready  first_norm")
     prev_end = None
     for i in range(n):
         r = t[i, :g].double()
@@ -56,18 +56,9 @@ def main():
         med = lambda c: float(((r[:, c] - r[:, 0])[r[:, c] > 0]).median()) / 1e3 if (r[:, c] > 0).any() else float("nan")
         wall = float(r[:, 5].max() - t0) / 1e3
         spread = float(r[:, 0].max() - t0) / 1e3
-        sm = r[:, 6].long()
-        # CTAs that overlap in time on one SM
-        per_sm = 1
-        for s_ in sm.unique():
-            q = r[sm == s_]
-            if len(q) > 1:
-                a0, a1 = q[:, 0], q[:, 5]
-                if bool(((a0[:, None] < a1[None, :]) & (a0[None, :] < a1[:, None])).sum() > len(q)):
-                    per_sm = 2
         gap = "" if prev_end is None else f" gap {float(t0 - prev_end) / 1e3:6.2f}"
         print(f"{i:4d}  {names[i % 4]:4s} {wall:6.2f}  {spread:8.2f}  {med(1):8.2f}  {med(2):8.2f}  {med(3):8.2f}  {med(4):8.2f}  "
-              f"{med(5):6.2f}  {per_sm:6d}  {int(r[:, 7].max()):6d}{gap}")
+              f"{med(5):6.2f}  {med(6):6.2f}  {med(7):6.2f}{gap}")
         prev_end = r[:, 5].max()
 
 
