@@ -143,10 +143,24 @@ def cpu_reference(steps: int, warmup: int):
     return cpu_baseline.measure(steps, warmup)
 
 
+def _timed_events(fn, steps, warmup=1):
+    for _ in range(warmup):
+        out = fn()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        out = fn()
+    ev1.record()
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1) / steps, out
+
+
 def voice_clone_bench(args):
     """BASELINE configs[4], single GPU: every step encodes the 10 s reference clips,
     builds the prompts (text ids + the reference's VQ columns + text ids), generates 512 frames per utterance
-    and decodes them to waveform — all through the public API, host audio in, host waveform out."""
+    and decodes them to waveform -- all through the public API, host audio in, host waveform out. The stages are
+    also timed one by one (device events, same inputs)."""
     from fish_speech_b200 import synthetic
     from fish_speech_b200.configs import S2PRO_IM_END_ID, s2pro_args
     from fish_speech_b200.models.dac.inference import load_codec_config
@@ -164,53 +178,239 @@ def voice_clone_bench(args):
     model.max_rows = 4096
     model.setup_caches(max_batch_size=B, max_seq_len=cfg.max_seq_len)
     del w
+    eng = model.engine
     ccfg = load_codec_config("modded_dac_vq")
     dac = DAC(ccfg, synthetic.codec_state_dict(ccfg, dev), device=dev)
     g = torch.Generator().manual_seed(0)
     audio_host = (0.1 * torch.randn(B, 1, 44100 * REF_S, generator=g)).pin_memory()
-    text_a = [torch.randint(0, 151643, (64,), generator=g, dtype=torch.int32) for _ in range(B)]
-    text_b = [torch.randint(0, 151643, (64,), generator=g, dtype=torch.int32) for _ in range(B)]
     C = cfg.num_codebooks
+    ta = torch.zeros(B, C + 1, 64, dtype=torch.int32)
+    tb = torch.zeros(B, C + 1, 64, dtype=torch.int32)
+    ta[:, 0] = torch.randint(0, 151643, (B, 64), generator=g, dtype=torch.int32)
+    tb[:, 0] = torch.randint(0, 151643, (B, 64), generator=g, dtype=torch.int32)
+    ta, tb = ta.to(dev), tb.to(dev)
     audio_lens = torch.full((B,), 44100 * REF_S, dtype=torch.long, device=dev)
+    T_REF = -(-44100 * REF_S // 2048)  # every clip has the same length here: no per-utterance host sync
+
+    def encode():
+        return dac.encode(audio_host.to(dev, non_blocking=True), audio_lens)[0]  # [B, 10, 216]
+
+    def prompts_of(codes):
+        vq = torch.zeros(B, C + 1, T_REF, dtype=torch.int32, device=dev)
+        vq[:, 0] = codes[:, 0, :T_REF].to(torch.int32) + cfg.semantic_begin_id
+        vq[:, 1:] = codes[:, :, :T_REF].to(torch.int32)
+        return list(torch.cat([ta, vq, tb], dim=2).unbind(0))
+
+    def generate(prompts):
+        return generate_batch(model=model, prompts=prompts, max_new_tokens=NF, temperature=0.7, top_p=0.7, top_k=1, seed=1)
 
     def step():
-        codes, lens = dac.encode(audio_host.to(dev, non_blocking=True), audio_lens)  # [B, 10, 216]
-        prompts = []
-        for b in range(B):
-            T = int(lens[b])
-            vq = torch.zeros(C + 1, T, dtype=torch.int32, device=dev)
-            vq[0] = codes[b, 0, :T].to(torch.int32) + cfg.semantic_begin_id
-            vq[1:] = codes[b, :, :T].to(torch.int32)
-            ta = torch.zeros(C + 1, 64, dtype=torch.int32, device=dev)
-            ta[0] = text_a[b].to(dev)
-            tb = torch.zeros(C + 1, 64, dtype=torch.int32, device=dev)
-            tb[0] = text_b[b].to(dev)
-            prompts.append(torch.cat([ta, vq, tb], dim=1))
-        outs = generate_batch(model=model, prompts=prompts, max_new_tokens=NF, temperature=0.7, top_p=0.7, top_k=1, seed=1)
-        gen = torch.stack([o[1:, p.shape[1]: p.shape[1] + NF] for o, p in zip(outs, prompts)]).contiguous()
-        return dac.from_indices(gen).cpu(), prompts[0].shape[1]
+        prompts = prompts_of(encode())
+        outs = generate(prompts)
+        plen = prompts[0].shape[1]
+        gen = torch.stack([o[1:, plen: plen + NF] for o in outs]).contiguous()
+        return dac.from_indices(gen).cpu(), plen
 
-    for _ in range(max(1, args.warmup)):
-        wav, plen = step()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(args.steps):
-        wav, plen = step()
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / args.steps
+    ms, (wav, plen) = _timed_events(step, args.steps, max(1, args.warmup))
+    # ---- stage breakdown ----
+    codes = encode()
+    prompts = prompts_of(codes)
+    sp = eng.sampling(0.7, 0.7, 1, 1)
+    enc_ms, _ = _timed_events(encode, 3)
+
+    def prefill():
+        eng.reset()
+        eng.prefill(prompts, list(range(B)), sp, do_sample=True)
+
+    pre_ms, _ = _timed_events(prefill, 3)
+    dec_ms, _ = _timed_events(lambda: eng.decode(B, 64, sp, use_graph=True), 2)
+    dec_ms /= 64
+    gen_codes = eng.buffer("out_tokens")[:B, 1:, :NF].contiguous()
+    cod_ms, _ = _timed_events(lambda: dac.from_indices(gen_codes), 3)
+    api_ms, _ = _timed_events(lambda: generate(prompts), 1)
     audio_s = B * NF * FRAME / SR
     v = audio_s / (ms / 1e3)
+    kv_per_tok = cfg.n_layer * 2 * cfg.n_local_heads * cfg.head_dim * 2
     print(json.dumps({
         "metric": "audio-sec/s", "value": v, "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": f"voice-clone: batch-{B}, {REF_S} s reference audio -> encode -> {plen}-position prefill -> "
                                f"{NF} frames -> waveform, S2-Pro geometry", "frames_per_s": B * NF / (ms / 1e3),
-                   "stages": ["codec_encode", "lm_prefill", "lm_decode", "codec_decode"]},
+                   "stages": ["codec_encode", "lm_prefill", "lm_decode", "codec_decode"],
+                   "stage_ms": {"codec_encode_8x10s": enc_ms, "lm_prefill": pre_ms, "lm_decode_per_frame": dec_ms,
+                                "lm_decode_511_frames": dec_ms * (NF - 1), "codec_decode": cod_ms,
+                                "generate_batch_api_call": api_ms,
+                                "sum_of_stages": enc_ms + pre_ms + dec_ms * (NF - 1) + cod_ms},
+                   "decode_floor_ms_per_frame": (15.55e9 + B * (plen + NF / 2) * kv_per_tok) / (peaks()[0]["hbm_gbs"] * 1e9) * 1e3},
         "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": audio_host.numel() * 4,
                 "d2h_bytes_per_step": wav.numel() * 4},
+    }))
+
+
+def single_stream_bench(args):
+    """BASELINE configs[1]: ONE 64-token prompt, greedy, 256 frames, LM stage: frames/s of a
+    single stream against the weight-streaming floor (15.55 GB per frame whatever the batch)."""
+    from fish_speech_b200 import synthetic
+    from fish_speech_b200.configs import S2PRO_IM_END_ID
+    from fish_speech_b200.models.text2semantic.inference import generate
+    from fish_speech_b200.models.text2semantic.llama import DualARTransformer
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    cfg = s2pro_cfg()
+    w = synthetic.lm_state_dict(cfg, dev)
+    w["embeddings.weight"][S2PRO_IM_END_ID] = 0
+    model = DualARTransformer(cfg, w, device=dev, im_end_id=S2PRO_IM_END_ID)
+    model.setup_caches(max_batch_size=1, max_seq_len=cfg.max_seq_len)
+    del w
+    eng = model.engine
+    prompt_host = make_prompts(cfg, 1, 42)[0].pin_memory()
+    sp = eng.sampling(0.7, 0.7, 1, 42)
+    NF = N_FRAMES
+
+    def api():
+        return generate(model=model, prompt=prompt_host.to(dev, non_blocking=True), max_new_tokens=NF, temperature=0.7,
+                        top_p=0.7, top_k=1, seed=42).cpu()
+
+    ms, out = _timed_events(api, args.steps, max(1, args.warmup))
+    eng.reset()
+    eng.prefill([prompt_host.to(dev)], [0], sp, do_sample=True)
+    dec_ms, _ = _timed_events(lambda: eng.decode(1, 100, sp, use_graph=True), 2)
+    dec_ms /= 100
+    pk, _ = peaks()
+    kv_per_tok = cfg.n_layer * 2 * cfg.n_local_heads * cfg.head_dim * 2
+    floor_ms = (15.55e9 + (T_PROMPT + 120) * kv_per_tok) / (pk["hbm_gbs"] * 1e9) * 1e3
+    v = NF * FRAME / SR / (ms / 1e3)
+    print(json.dumps({
+        "metric": "audio-sec/s", "value": v, "unit": "audio-s/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "S2-Pro 4B Dual-AR greedy decode, single 64-token prompt, 256 frames, LM stage, 1 GPU",
+                   "frames_per_s": NF / (ms / 1e3), "codec_tokens_per_s": NF * cfg.num_codebooks / (ms / 1e3),
+                   "ms_per_decode_frame": dec_ms, "hbm_floor_ms_per_frame": floor_ms, "hbm_frac": floor_ms / dec_ms,
+                   "generated": list(out.shape)},
+        "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": prompt_host.numel() * 4,
+                "d2h_bytes_per_step": out.numel() * 8},
+    }))
+
+
+def roundtrip_bench(args):
+    """BASELINE configs[0]: Firefly VQ-GAN encode -> decode of 1 s of 44.1 kHz audio, host
+    waveform in, host waveform out, beside the reference's CPU path (oracle/cpu_baseline.py codec) on the host cores."""
+    from fish_speech_b200 import synthetic
+    from fish_speech_b200.models.dac.inference import load_codec_config
+    from fish_speech_b200.models.dac.modded_dac import DAC
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    ccfg = load_codec_config("modded_dac_vq")
+    dac = DAC(ccfg, synthetic.codec_state_dict(ccfg, dev), device=dev)
+    g = torch.Generator().manual_seed(0)
+    wav_host = (0.1 * torch.randn(1, 1, 44100, generator=g)).pin_memory()
+
+    def step():
+        codes, lens = dac.encode(wav_host.to(dev, non_blocking=True))
+        return dac.from_indices(codes).cpu(), codes
+
+    ms, (wav, codes) = _timed_events(step, max(args.steps, 10), 3)
+    enc_ms, _ = _timed_events(lambda: dac.encode(wav_host.to(dev)), 10, 2)
+    dec_ms, _ = _timed_events(lambda: dac.from_indices(codes), 10, 2)
+    cpu = None
+    if not args.no_cpu_baseline:
+        import time
+
+        from oracle import codec_oracle as CO
+        from oracle import cpu_baseline
+
+        torch.set_num_threads(min(cpu_baseline.usable_cores(), 32))
+        oc = CO.full_config()
+        ow = CO.make_weights(oc, seed=6)
+        with torch.inference_mode():
+            CO.encode(ow, oc, wav_host.clone())  # warm-up
+            t0 = time.perf_counter()
+            c2, _ = CO.encode(ow, oc, wav_host.clone())
+            t1 = time.perf_counter()
+            CO.from_indices(ow, oc, c2)
+            t2 = time.perf_counter()
+        cpu = {"value": 1.0 / (t2 - t0), "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"the same 1 s clip, fp32: encode {1e3 * (t1 - t0):.0f} ms + decode {1e3 * (t2 - t1):.0f} ms"}
+    v = (codes.shape[-1] * FRAME / SR) / (ms / 1e3)
+    print(json.dumps({
+        "metric": "audio-sec/s", "value": v, "unit": "audio-s/s", "n_gpus": 1, "steps": max(args.steps, 10), "warmup": 3,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "Firefly VQ-GAN (391 M DAC) encode -> decode roundtrip, 1 s 44.1 kHz mono, batch 1",
+                   "stage_ms": {"encode": enc_ms, "decode": dec_ms}, "codes": list(codes.shape)},
+        "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": wav_host.numel() * 4, "d2h_bytes_per_step": wav.numel() * 4},
+        "cpu_baseline": cpu,
+    }))
+
+
+def stream_bench(args):
+    """time to first audio of ONE utterance (64-token prompt, 256 frames) with the codec decoding every
+    8 frames on a second CUDA stream while the LM keeps decoding (generate(frame_callback) + DAC.open_decode_stream),
+    against decoding the codes after the LM has finished (the reference's order, inference_engine/__init__.py:84-119)."""
+    import time
+
+    from fish_speech_b200 import synthetic
+    from fish_speech_b200.configs import S2PRO_IM_END_ID
+    from fish_speech_b200.models.dac.inference import load_codec_config
+    from fish_speech_b200.models.dac.modded_dac import DAC
+    from fish_speech_b200.models.text2semantic.inference import generate
+    from fish_speech_b200.models.text2semantic.llama import DualARTransformer
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    cfg = s2pro_cfg()
+    w = synthetic.lm_state_dict(cfg, dev)
+    w["embeddings.weight"][S2PRO_IM_END_ID] = 0
+    model = DualARTransformer(cfg, w, device=dev, im_end_id=S2PRO_IM_END_ID)
+    model.setup_caches(max_batch_size=1, max_seq_len=cfg.max_seq_len)
+    del w
+    ccfg = load_codec_config("modded_dac_vq")
+    dac = DAC(ccfg, synthetic.codec_state_dict(ccfg, dev), device=dev)
+    prompt = make_prompts(cfg, 1, 42)[0].to(dev)
+    NF = N_FRAMES
+    side = torch.cuda.Stream(device=dev)
+    kw = dict(model=model, prompt=prompt, max_new_tokens=NF, temperature=0.7, top_p=0.7, top_k=1, seed=42)
+
+    def streamed():
+        st = dac.open_decode_stream(batch=1, max_frames=NF + 8)
+        t0 = time.perf_counter()
+        first, pieces = [None], []
+
+        def cb(b, codes):
+            with torch.cuda.stream(side):
+                wav = st.push(codes[None].to(dev)).cpu()
+            if first[0] is None:
+                first[0] = time.perf_counter() - t0
+            pieces.append(wav)
+
+        y = generate(frame_callback=cb, **kw)
+        total = time.perf_counter() - t0
+        return first[0], total, torch.cat(pieces, dim=-1), y
+
+    def after():
+        t0 = time.perf_counter()
+        y = generate(**kw)
+        wav = dac.from_indices(y[None, 1:, T_PROMPT:-1].contiguous()).cpu()
+        return time.perf_counter() - t0, wav
+
+    for _ in range(2):
+        streamed()
+        after()
+    fa, tot, wav_s, y = streamed()
+    t_after, wav_a = after()
+    same = wav_s.shape == wav_a.shape and float((wav_s - wav_a).abs().max()) < 1e-3
+    print(json.dumps({
+        "metric": "time-to-first-audio", "value": fa * 1e3, "unit": "ms", "n_gpus": 1, "steps": 1, "warmup": 2,
+        "ms_per_step": tot * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "1 utterance, 64-token prompt, 256 frames, codec decoded every 8 frames while the LM decodes",
+                   "first_audio_ms_streaming": fa * 1e3, "total_ms_streaming": tot * 1e3,
+                   "first_audio_ms_decode_after_lm": t_after * 1e3, "audio_s": (NF - 1) * FRAME / SR,
+                   "same_waveform": bool(same)},
     }))
 
 
@@ -300,7 +500,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-codec", action="store_true", help="time the LM stages only")
     ap.add_argument("--profile-only", action="store_true", help="run the timed step once and exit (for ncu)")
-    ap.add_argument("--workload", default="batch32", choices=["batch32", "voice-clone", "serve"],
+    ap.add_argument("--workload", default="batch32", choices=["batch32", "voice-clone", "serve", "single", "roundtrip", "stream"],
                     help="batch32 = BASELINE configs[2] (the headline); voice-clone = configs[4]: 10 s reference "
                          "audio -> codec encode -> ~350-position prefill -> 512 frames -> waveform, batch 8")
     args = ap.parse_args()
@@ -315,6 +515,8 @@ def main():
         return voice_clone_bench(args)
     if args.workload == "serve" and args.impl != "reference":
         return serve_bench(args)
+    if args.workload in ("single", "roundtrip", "stream") and args.impl != "reference":
+        return {"single": single_stream_bench, "roundtrip": roundtrip_bench, "stream": stream_bench}[args.workload](args)
     if args.impl == "reference":
         if rank != 0:
             return

@@ -65,7 +65,7 @@ def read_audio(path: Path) -> tuple[torch.Tensor, int]:
 
         data, sr = sf.read(str(path), dtype="float32", always_2d=True)
         return torch.from_numpy(data).mean(dim=1), int(sr)
-    except ImportError:
+    except Exception:  # not installed, or a format libsndfile cannot decode: the next reader may
         pass
     try:
         import torchaudio

@@ -11,9 +11,9 @@
 //   step_ws            fp32 stream-K partials of the step GEMMs: [slot][tile][32 rows][128 features]
 //   prefill workspaces [max_rows][*] operands + ws fp32 [max_rows][N]
 //
-// One decode frame (inference.py:96-181) = embed, 36 x {qkv GEMM, attention (finishes qkv: bias / qk-norm / RoPE /
-// KV append), wo GEMM, w1|w3 GEMM (prologue: wo's residual add; norm on load), w2 GEMM (prologue: SwiGLU)}, head GEMM
-// (prologue: the last residual add) + sampler, then 10 fast passes of 4 such layers each: ~410 kernels, five per
+// One decode frame (inference.py:96-181) = embed, 36 x {qkv GEMM (norm on load), attention (finishes qkv: bias /
+// qk-norm / RoPE / KV append), wo GEMM, finalize (residual add), w1|w3 GEMM (norm on load), finalize (SwiGLU), w2 GEMM,
+// finalize (residual add)}, head GEMM + sampler, then 10 fast passes of 4 such layers each: ~640 kernels, eight per
 // layer; every GEMM only stores fp32 partials, its consumer finishes it (lm_gemm.cuh).
 //
 // Reference: fish_speech/models/text2semantic/llama.py:390-466 (slow step), :799-817 (fast step),
@@ -77,7 +77,6 @@ struct fsb_lm {
     fsb_lm_config cfg;
     int num_sms = 148;
     int step_ctas = 0, step_stages = 4;
-    bool fused_prologue = true;  // finish each GEMM in its consumer's prologue (else: in a kernel of its own)
     Stack slow, fast;
     const bf16 *emb = nullptr, *cb_emb = nullptr, *norm_w = nullptr, *head_w = nullptr;
     const bf16 *fast_emb = nullptr, *fast_norm_w = nullptr, *fast_out_w = nullptr;
@@ -89,7 +88,6 @@ struct fsb_lm {
     bf16 *q_d = nullptr, *attn_d = nullptr, *h_d = nullptr, *hid_d = nullptr;
     float* step_ws = nullptr;
     size_t step_ws_floats = 0;
-    unsigned* grid_bar = nullptr;  // arrival counter + generation words of the step GEMM prologues
     // prefill workspaces
     bf16 *xres_p = nullptr, *xn_p = nullptr, *q_p = nullptr, *attn_p = nullptr, *h_p = nullptr;
     float* ws = nullptr;
@@ -159,12 +157,11 @@ int launch_rows_of(const GemmPlan& plan, int rows, cudaStream_t st) {
 
 // Step GEMM over the weight `w` [n_out, K]. act != null: operand X = act, used as it is; act == null: operand X = the
 // stack's residual stream, normalised on load (bind_norm_on_load supplies the norm).
-int make_step_plan(fsb_lm* h, StepGemmPlan* plan, int pro, const bf16* w, int n_out, int K, const bf16* act,
+int make_step_plan(fsb_lm* h, StepGemmPlan* plan, const bf16* w, int n_out, int K, const bf16* act,
                    const Stack* norm_of = nullptr) {
     const bool norm = act == nullptr;
     if (norm) act = norm_of->xres;
-    return step_plan_init(plan, pro, w, n_out, K, act, norm, h->step_ctas, h->step_stages, h->step_ws,
-                          h->step_ws_floats, h->grid_bar);
+    return step_plan_init(plan, w, n_out, K, act, norm, h->step_ctas, h->step_stages, h->step_ws, h->step_ws_floats);
 }
 
 void bind_norm_on_load(StepGemmPlan* plan, const Stack& s, const bf16* norm_w, float eps) {
@@ -174,9 +171,9 @@ void bind_norm_on_load(StepGemmPlan* plan, const Stack& s, const bf16* norm_w, f
     plan->p.eps = eps;
 }
 
-// PRO_RESID prologue of `plan`: finish `prev` (a Linear whose output is added to the residual stream of stack s)
+// `plan` reads the residual stream of stack s after `prev` (a Linear) has been added to it: PRO_RESID finalize of prev
 void bind_resid(StepGemmPlan* plan, const StepGemmPlan& prev, const Stack& s, const bf16* bias, bool add_residual) {
-    step_plan_set_prev(plan, prev);
+    step_plan_set_prev(plan, PRO_RESID, prev);
     plan->p.bias = bias;
     plan->p.resid = add_residual ? s.xres : nullptr;
     plan->p.x_out = s.xres;
@@ -202,15 +199,11 @@ SlotCtl slot_ctl(const fsb_lm* h) {
 int run_stack_decode(fsb_lm* h, Stack& s, int rows, const int* row_seq, const int* row_pos, bool stop_after_kv,
                      cudaStream_t st, const StepGemmPlan* first_qkv = nullptr) {
     const float eps = h->cfg.norm_eps;
-    // a step GEMM whose prologue finishes its producer; with FSB_PROLOGUE=0 the same work runs as a kernel of its own
-    // in front of the GEMM, which then finds its operand complete
+    // finish the producer of the operand (residual add / SwiGLU), then the GEMM itself
     auto launch = [&](const StepGemmPlan& plan) -> int {
         StepGemmPlan q = plan;
         q.p.rows = rows;
-        if (q.pro != PRO_NONE && !h->fused_prologue) {
-            FSB_TRY(step_finalize_launch(q, q.pro, st));
-            q.pro = PRO_NONE;
-        }
+        FSB_TRY(step_finalize_launch(q, st));
         return step_gemm_launch(q, st);
     };
     for (int l = 0; l < s.nl; ++l) {
@@ -317,10 +310,7 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
     auto launch = [&](const StepGemmPlan& plan) -> int {
         StepGemmPlan q = plan;
         q.p.rows = rows;
-        if (q.pro != PRO_NONE && !h->fused_prologue) {
-            FSB_TRY(step_finalize_launch(q, q.pro, st));
-            q.pro = PRO_NONE;
-        }
+        FSB_TRY(step_finalize_launch(q, st));
         return step_gemm_launch(q, st);
     };
     auto sample_args = [&](int n, const StepGemmPlan& head) {
@@ -340,7 +330,7 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
         a.noise_ld = h->noise_ld;
         return a;
     };
-    // ---- slow head over the selectable rows (its prologue adds the last layer's FFN output to the residual stream
+    // ---- slow head over the selectable rows (first the last layer's FFN output is added to the residual stream,
     // unless the rows come from a prefill; the final norm is applied on load) ----
     const StepGemmPlan& head = x_is_final ? h->head_plan_direct : h->head_plan;
     FSB_TRY(launch(head));
@@ -368,7 +358,7 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
     if (h->has_proj) {
         hr.y = h->hid_d;
         FSB_TRY(launch_rows(hr, st));
-        FSB_TRY(launch(h->proj_plan));  // fast_project_in; layer 0's qkv GEMM adds the bias in its prologue
+        FSB_TRY(launch(h->proj_plan));  // fast_project_in; the finalize in front of layer 0's qkv GEMM adds the bias
     } else {
         hr.y = f.xres;
         hr.ssq = f.ssq;
@@ -472,10 +462,6 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     }
     {
         // ring depth / CTAs per SM of the step GEMMs are tunable for experiments
-        // measured on B200 (batch 32, S2-Pro geometry): finishing each GEMM in a small kernel of its own = 5.5 ms per frame,
-        // in the consumer GEMM's prologue behind a grid-wide arrival = 6.2 ms (the arrival waits for the last CTA to start)
-        const char* ep = getenv("FSB_PROLOGUE");
-        h->fused_prologue = ep && ep[0] == '1';
         const char* es = getenv("FSB_STAGES");
         const char* ec = getenv("FSB_CTAS_PER_SM");
         h->step_stages = es ? atoi(es) : 4;
@@ -535,7 +521,6 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     } while (0)
     TRYC(dalloc(h, &h->ws, h->ws_floats));
     TRYC(dalloc(h, &h->step_ws, h->step_ws_floats));
-    TRYC(dalloc(h, &h->grid_bar, 32 * 9));  // arrival counter + 8 generation words, one L2 line each
     TRYC(dalloc(h, &s.xres, static_cast<size_t>(kDecRows) * s.D));
     TRYC(dalloc(h, &s.ssq, static_cast<size_t>(kDecRows) * kSsqStride));
     TRYC(dalloc(h, &f.xres, static_cast<size_t>(kDecRows) * f.D));
@@ -596,15 +581,15 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
             const LayerW& lw = st.w[l];
             StepLayer& P = st.dec[l];
             // qkv: layer 0 reads a residual stream a row kernel wrote; later layers first add the previous FFN output
-            FSB_TRY(make_step_plan(h, &P.qkv, l == 0 ? PRO_NONE : PRO_RESID, lw.wqkv, Nqkv, st.D, nullptr, &st));
+            FSB_TRY(make_step_plan(h, &P.qkv, lw.wqkv, Nqkv, st.D, nullptr, &st));
             bind_norm_on_load(&P.qkv, st, lw.attn_norm, eps);
             if (l > 0) bind_resid(&P.qkv, st.dec[l - 1].w2, st, nullptr, true);
-            FSB_TRY(make_step_plan(h, &P.wo, PRO_NONE, lw.wo, st.D, st.H * st.Dh, h->attn_d));
-            FSB_TRY(make_step_plan(h, &P.w13, PRO_RESID, lw.w13, st.n13, st.D, nullptr, &st));
+            FSB_TRY(make_step_plan(h, &P.wo, lw.wo, st.D, st.H * st.Dh, h->attn_d));
+            FSB_TRY(make_step_plan(h, &P.w13, lw.w13, st.n13, st.D, nullptr, &st));
             bind_norm_on_load(&P.w13, st, lw.ffn_norm, eps);
             bind_resid(&P.w13, P.wo, st, lw.bo, true);
-            FSB_TRY(make_step_plan(h, &P.w2, PRO_SWIGLU, lw.w2, st.D, st.I, h->h_d));
-            step_plan_set_prev(&P.w2, P.w13);
+            FSB_TRY(make_step_plan(h, &P.w2, lw.w2, st.D, st.I, h->h_d));
+            step_plan_set_prev(&P.w2, PRO_SWIGLU, P.w13);
             P.w2.p.h = h->h_d;
             P.w2.p.I = st.I;
             if (with_prefill) {
@@ -618,19 +603,19 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
     };
     TRYC(build(s, true));
     TRYC(build(f, false));
-    TRYC(make_step_plan(h, &h->head_plan, PRO_RESID, h->head_w, h->head_rows, s.D, nullptr, &s));
+    TRYC(make_step_plan(h, &h->head_plan, h->head_w, h->head_rows, s.D, nullptr, &s));
     bind_norm_on_load(&h->head_plan, s, h->norm_w, eps);
     bind_resid(&h->head_plan, s.dec[s.nl - 1].w2, s, nullptr, true);
-    TRYC(make_step_plan(h, &h->head_plan_direct, PRO_NONE, h->head_w, h->head_rows, s.D, nullptr, &s));
+    TRYC(make_step_plan(h, &h->head_plan_direct, h->head_w, h->head_rows, s.D, nullptr, &s));
     bind_norm_on_load(&h->head_plan_direct, s, h->norm_w, eps);
-    TRYC(make_step_plan(h, &h->fast_out_plan, PRO_RESID, h->fast_out_w, cfg->codebook_size, f.D, nullptr, &f));
+    TRYC(make_step_plan(h, &h->fast_out_plan, h->fast_out_w, cfg->codebook_size, f.D, nullptr, &f));
     bind_norm_on_load(&h->fast_out_plan, f, h->fast_norm_w, eps);
     bind_resid(&h->fast_out_plan, f.dec[f.nl - 1].w2, f, nullptr, true);
     if (h->has_proj) {
-        TRYC(make_step_plan(h, &h->proj_plan, PRO_NONE, h->fast_proj_w, f.D, s.D, h->hid_d));
+        TRYC(make_step_plan(h, &h->proj_plan, h->fast_proj_w, f.D, s.D, h->hid_d));
         // fast layer 0 of pass 0: its operand = fast_project_in(hidden) + bias, finished in the qkv GEMM's prologue
         const LayerW& l0 = f.w[0];
-        TRYC(make_step_plan(h, &h->fast_qkv0_proj, PRO_RESID, l0.wqkv, (f.H + 2 * f.Hkv) * f.Dh, f.D, nullptr, &f));
+        TRYC(make_step_plan(h, &h->fast_qkv0_proj, l0.wqkv, (f.H + 2 * f.Hkv) * f.Dh, f.D, nullptr, &f));
         bind_norm_on_load(&h->fast_qkv0_proj, f, l0.attn_norm, eps);
         bind_resid(&h->fast_qkv0_proj, h->proj_plan, f, h->fast_proj_b, false);
     }
@@ -794,6 +779,7 @@ int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* l
         ++launches;
         StepGemmPlan q = p;
         q.p.rows = rows;
+        FSB_TRY(step_finalize_launch(q, st));
         return step_gemm_launch(q, st);
     };
     for (int r = 0; r < reps; ++r) {

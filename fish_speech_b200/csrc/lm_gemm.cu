@@ -21,7 +21,7 @@ constexpr int kBTileBytes = kBN * kBlockK * 2;  // 4 KB
 constexpr int kStageBytes = kATileBytes + kBTileBytes;
 constexpr int kTmemCols = 2 * kBN;  // two accumulators: the stores of item n overlap the MMAs of item n+1
 constexpr int kEpiThreads = 128;
-constexpr int kLoaderThreads = 64;
+constexpr int kLoaderThreads = 128;  // four normaliser warps: two 16-byte cells per thread and k-block
 constexpr int kScratchBytes = 1024;  // r_s[32] | red[4][32]
 
 __device__ __forceinline__ void bar_sync(int id, int n) {
@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(kEpiThreads) step_finalize_kernel(const __grid
     }
 }
 
-template <int PRO, int NORM>
-__global__ void __launch_bounds__(NORM ? 256 : 192, 2)
+template <int NORM>
+__global__ void __launch_bounds__(NORM ? 192 + kLoaderThreads : 192, 2)
 step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ StepGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -160,10 +160,10 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int stages = p.stages;
     const uint32_t bars = tiles + static_cast<uint32_t>(stages) * kStageBytes;
     // barrier block: full[stages] (tile ready for the MMA), empty[stages], rawx[stages] (un-normalised X landed),
-    // tmem_full[2], tmem_empty[2], xready (operand complete grid-wide), TMEM base word
+    // tmem_full[2], tmem_empty[2], TMEM base word
     const uint32_t full0 = bars, empty0 = bars + 8u * stages, rawx0 = bars + 16u * stages;
-    const uint32_t tfull0 = bars + 24u * stages, tempty0 = tfull0 + 16u, xready = tempty0 + 16u;
-    const uint32_t tmem_slot = xready + 8u;
+    const uint32_t tfull0 = bars + 24u * stages, tempty0 = tfull0 + 16u;
+    const uint32_t tmem_slot = tempty0 + 16u + 8u;
     const int scratch_off = ((24 * stages + 56 + 15) / 16) * 16;
     uint8_t* gen = smem_raw + (tiles - raw);
     uint8_t* bar_gen = gen + static_cast<size_t>(stages) * kStageBytes;
@@ -195,7 +195,6 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(tfull0 + 8u * a, 1);
             mbar_init(tempty0 + 8u * a, 4);  // one arrival per epilogue warp
         }
-        mbar_init(xready, 1);
         fence_mbar_init();
     }
     if (warp == 5) tmem_alloc(tmem_slot, kTmemCols);
@@ -246,10 +245,6 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             pdl_wait();
             if (trace) trace[1] = globaltimer_ns();
-            if (PRO != PRO_NONE) {
-                mbar_wait(xready, 0);  // every CTA's prologue units are done: the operand is complete
-                asm volatile("fence.proxy.async;" ::: "memory");  // other CTAs' generic stores -> this CTA's TMA reads
-            }
             int it = 0;
             for (int n = item_begin; n < item_end; ++n) {
                 const int4 w = p.sched[n];
@@ -304,13 +299,12 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp >= 6) {
         // ===== operand-X normalisers: rbf(rbf(x * r_row) * w) in place on the swizzled tile TMA delivered =====
         if (NORM) {
-            const int t = threadIdx.x - 192;  // 0..63
+            const int t = threadIdx.x - 192;  // 0..127
             // the norm weights are constants: stage them before waiting for the upstream kernel
             const int nchunks = ((p.K + kBlockK - 1) / kBlockK) * 8;
             for (int ch = t; ch < nchunks; ch += kLoaderThreads)
                 normw_s[ch] = ch * 8 < p.K ? __ldg(reinterpret_cast<const uint4*>(p.norm_w + ch * 8)) : make_uint4(0, 0, 0, 0);
             pdl_wait();
-            if (PRO != PRO_NONE) mbar_wait(xready, 0);
             if (t < 32) {
                 // rsqrt(mean(x^2) + eps) of row t: the producer's per-tile sums, added in tile order (all loads in flight)
                 // (16-byte loads: every CTA of the grid reads these same 32 lines right after the grid-wide arrival)
@@ -330,13 +324,14 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             bar_sync(2, kLoaderThreads);
             if (trace && t == 0) trace[6] = globaltimer_ns();
-            // 32 rows x 8 sixteen-byte chunks per k-block; thread t owns chunk (t & 7) of rows (t >> 3) + 8e
+            // 32 rows x 8 sixteen-byte chunks per k-block; thread t owns chunk (t & 7) of rows (t >> 3) + 16e
+            constexpr int kCells = 256 / kLoaderThreads;
             const int c = t & 7, rb = t >> 3;
-            float rr[4];
-            uint32_t off[4];
+            float rr[kCells];
+            uint32_t off[kCells];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int row = rb + 8 * e;
+            for (int e = 0; e < kCells; ++e) {
+                const int row = rb + (kLoaderThreads / 8) * e;
                 rr[e] = r_s[row];
                 off[e] = static_cast<uint32_t>(row * 128 + ((c ^ (row & 7)) << 4));  // SWIZZLE_128B
             }
@@ -352,7 +347,7 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     uint8_t* btile = gen + static_cast<size_t>(s) * kStageBytes + kATileBytes;
                     mbar_wait(rawx0 + 8u * s, ph);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
+                    for (int e = 0; e < kCells; ++e) {
                         uint4* cell = reinterpret_cast<uint4*>(btile + off[e]);
                         const uint4 xv = *cell;
                         const float xf[8] = {bf_lo(xv.x), bf_hi(xv.x), bf_lo(xv.y), bf_hi(xv.y),
@@ -375,48 +370,9 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        // ===== warps 0-3: prologue, then the partial stores =====
+        // ===== warps 0-3: TMEM -> registers -> fp32 partial stores =====
         const int tid = threadIdx.x;  // 0..127 = TMEM lane = feature inside the tile
         pdl_wait();
-        if (PRO != PRO_NONE) {
-            // waiters poll one of 8 copies of a generation word (32 words apart: separate L2 lines), never the arrival
-            // counter: the value before this CTA arrives is read here
-            volatile unsigned* flag = p.grid_bar + 32 * (1 + (blockIdx.x & 7));
-            const unsigned gen0 = tid == 0 ? *flag : 0u;
-            switch (p.prev_rb) {
-                case 1: pro_units<PRO, 1>(p, tid, red); break;
-                case 2: pro_units<PRO, 2>(p, tid, red); break;
-                case 4: pro_units<PRO, 4>(p, tid, red); break;
-                case 8: pro_units<PRO, 8>(p, tid, red); break;
-                case 16: pro_units<PRO, 16>(p, tid, red); break;
-                default: pro_units<PRO, 32>(p, tid, red); break;
-            }
-            if (trace && tid == 0) trace[2] = globaltimer_ns();
-            bar_sync(1, kEpiThreads);
-            if (tid == 0) {
-                // Grid-wide "operand complete": every CTA of this launch is resident (the grid fits the GPU in one
-                // wave) and arrives without waiting for anybody, so the spin is bounded; a protocol bug becomes a
-                // trap instead of a hung GPU.
-                __threadfence();  // cumulative: the stores of all 128 threads (joined by the barrier) before the arrival
-                if (atomicAdd(p.grid_bar, 1u) == gridDim.x - 1) {
-                    // last one in: re-arm the counter for the next launch and publish the new generation
-                    p.grid_bar[0] = 0;
-                    __threadfence();
-                    for (int k = 0; k < 8; ++k) atomicExch(p.grid_bar + 32 * (1 + k), gen0 + 1);
-                } else {
-                    const long long t0 = clock64();
-                    while (ld_acquire_gpu(const_cast<const unsigned*>(flag)) == gen0) {
-                        __nanosleep(40);
-                        if (clock64() - t0 > 4000000000ll) {
-                            printf("fsb: step GEMM arrival timeout block=%d have=%u want=%u\n", blockIdx.x, *p.grid_bar, gridDim.x);
-                            __trap();
-                        }
-                    }
-                }
-                if (trace) trace[3] = globaltimer_ns();
-                mbar_arrive(xready);
-            }
-        }
         for (int n = item_begin; n < item_end; ++n) {
             const int4 w = p.sched[n];
             const int tile = w.x, slot = w.w;
@@ -447,19 +403,15 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-template <int PRO, int NORM>
+template <int NORM>
 int launch_t(const StepGemmPlan& plan, cudaStream_t st) {
-    auto k = step_gemm_kernel<PRO, NORM>;
-    FSB_LAUNCH(k, plan.grid, dim3(NORM ? 256 : 192), plan.smem, st, plan.tmA, plan.tmB, plan.p);
+    auto k = step_gemm_kernel<NORM>;
+    FSB_LAUNCH(k, plan.grid, dim3(NORM ? 192 + kLoaderThreads : 192), plan.smem, st, plan.tmA, plan.tmB, plan.p);
     return 0;
 }
 
-const void* kernel_of(int pro, int norm) {
-    if (pro == PRO_NONE && norm) return reinterpret_cast<const void*>(step_gemm_kernel<PRO_NONE, 1>);
-    if (pro == PRO_NONE && !norm) return reinterpret_cast<const void*>(step_gemm_kernel<PRO_NONE, 0>);
-    if (pro == PRO_RESID && norm) return reinterpret_cast<const void*>(step_gemm_kernel<PRO_RESID, 1>);
-    if (pro == PRO_SWIGLU && !norm) return reinterpret_cast<const void*>(step_gemm_kernel<PRO_SWIGLU, 0>);
-    return nullptr;
+const void* kernel_of(int norm) {
+    return norm ? reinterpret_cast<const void*>(step_gemm_kernel<1>) : reinterpret_cast<const void*>(step_gemm_kernel<0>);
 }
 
 }  // namespace
@@ -467,24 +419,23 @@ const void* kernel_of(int pro, int norm) {
 int step_gemm_init() {
     static bool done = false;
     if (done) return 0;
-#define FSB_STEP_ATTR(E_, B_)                                                                                          \
-    FSB_CUDA(cudaFuncSetAttribute(step_gemm_kernel<E_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-    FSB_CUDA(cudaFuncSetAttribute(step_gemm_kernel<E_, B_>, cudaFuncAttributePreferredSharedMemoryCarveout,            \
+#define FSB_STEP_ATTR(B_)                                                                                          \
+    FSB_CUDA(cudaFuncSetAttribute(step_gemm_kernel<B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    FSB_CUDA(cudaFuncSetAttribute(step_gemm_kernel<B_>, cudaFuncAttributePreferredSharedMemoryCarveout,            \
                                   cudaSharedmemCarveoutMaxShared));
-    FSB_STEP_ATTR(PRO_NONE, 1) FSB_STEP_ATTR(PRO_NONE, 0) FSB_STEP_ATTR(PRO_RESID, 1) FSB_STEP_ATTR(PRO_SWIGLU, 0)
+    FSB_STEP_ATTR(1) FSB_STEP_ATTR(0)
 #undef FSB_STEP_ATTR
     done = true;
     return 0;
 }
 
-int step_plan_init(StepGemmPlan* plan, int pro, const __nv_bfloat16* w, int n_out, int K, const __nv_bfloat16* act,
-                   bool norm_on_load, int num_ctas, int stages, float* ws, size_t ws_floats, unsigned* grid_bar) {
+int step_plan_init(StepGemmPlan* plan, const __nv_bfloat16* w, int n_out, int K, const __nv_bfloat16* act,
+                   bool norm_on_load, int num_ctas, int stages, float* ws, size_t ws_floats) {
     memset(plan, 0, sizeof(*plan));
     FSB_CHECK(K % 8 == 0, "step GEMM: K=%d must be a multiple of 8", K);
     FSB_CHECK(act != nullptr, "step GEMM: operand X missing");
     const int norm = norm_on_load ? 1 : 0;
-    const void* kernel = kernel_of(pro, norm);
-    FSB_CHECK(kernel != nullptr, "step GEMM: unsupported prologue %d / norm %d combination", pro, norm);
+    const void* kernel = kernel_of(norm);
     FSB_TRY(step_gemm_init());
     GemmOperand A{w, K, n_out, 1, K, static_cast<long long>(n_out) * K};
     FSB_TRY(gemm_make_tmap(&plan->tmA, A, kBlockM));
@@ -498,9 +449,9 @@ int step_plan_init(StepGemmPlan* plan, int pro, const __nv_bfloat16* w, int n_ou
     };
     while (stages > 2 && 2 * (smem_of(stages) + 1024) > 228 * 1024) --stages;  // two CTAs per SM
     FSB_CHECK(stages >= 2, "step GEMM: ring too shallow");
-    // The prologue's grid-wide arrival needs the whole grid resident at once. cudaOccupancyMaxActiveBlocksPerMultiprocessor
-    // reports 1 for every kernel that allocates tensor memory, although two such CTAs do share an SM (verified with
-    // %smid stamps, tools/trace_step_gemms.py): count registers and shared memory ourselves.
+    // One wave: the stream-K ranges assume every CTA runs at once. cudaOccupancyMaxActiveBlocksPerMultiprocessor reports
+    // 1 for every kernel that allocates tensor memory, although two such CTAs do share an SM (verified with %smid
+    // stamps): count registers and shared memory ourselves.
     int dev = 0, sms = 0, smem_sm = 0, regs_sm = 0, resv = 0;
     FSB_CUDA(cudaGetDevice(&dev));
     FSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -509,7 +460,7 @@ int step_plan_init(StepGemmPlan* plan, int pro, const __nv_bfloat16* w, int n_ou
     FSB_CUDA(cudaDeviceGetAttribute(&resv, cudaDevAttrReservedSharedMemoryPerBlock, dev));
     cudaFuncAttributes fa;
     FSB_CUDA(cudaFuncGetAttributes(&fa, kernel));
-    const int threads = norm ? 256 : 192;
+    const int threads = norm ? 192 + kLoaderThreads : 192;
     const int regs_cta = ((fa.numRegs + 7) / 8) * 8 * threads;
     const int per_sm = std::min<int>(regs_sm / regs_cta, smem_sm / static_cast<int>(smem_of(stages) + resv + fa.sharedSizeBytes));
     FSB_CHECK(per_sm >= 1, "step GEMM: kernel does not fit an SM (smem %zu, %d registers)", smem_of(stages), fa.numRegs);
@@ -554,7 +505,6 @@ int step_plan_init(StepGemmPlan* plan, int pro, const __nv_bfloat16* w, int n_ou
     p.a_hint = kEvictFirst;  // weights are streamed once per step (>> L2)
     p.b_hint = kEvictLast;   // the activation tile is re-read by every CTA
     p.ws = ws;
-    p.grid_bar = grid_bar;
     p.prev_rb = 32;
     {
         const char* e = getenv("FSB_L2_PREFETCH");
@@ -562,7 +512,7 @@ int step_plan_init(StepGemmPlan* plan, int pro, const __nv_bfloat16* w, int n_ou
     }
     plan->grid = dim3(static_cast<unsigned>(num_ctas), 1, 1);
     plan->smem = smem_of(stages);
-    plan->pro = pro;
+    plan->pro = PRO_NONE;
     plan->norm = norm;
     plan->weight_bytes = static_cast<double>(n_out) * K * 2;
     return 0;
@@ -577,23 +527,9 @@ StepPartials step_plan_partials(const StepGemmPlan& plan) {
     return P;
 }
 
-void step_plan_set_prev(StepGemmPlan* plan, const StepGemmPlan& prev) {
+void step_plan_set_prev(StepGemmPlan* plan, int pro, const StepGemmPlan& prev) {
     plan->p.prev = step_plan_partials(prev);
-    // rows per prologue unit: fewest sequential L2 round trips for the slowest CTA =
-    //   ceil(units / grid) passes  x  ceil(max_parts / (32 / rb)) load rounds per unit; ties -> more CTAs busy
-    const int grid = static_cast<int>(plan->grid.x);
-    int best_rb = 32;
-    long long best = 1ll << 40;
-    for (int rb = 32; rb >= 1; rb >>= 1) {
-        const long long units = static_cast<long long>(prev.p.tiles) * cdiv(kStepRows, rb);
-        const int uq = (rb == 32 && plan->pro == PRO_SWIGLU) ? 2 : 32 / rb;  // partials per load round (prev_sums)
-        const long long cost = cdivll(units, grid) * cdiv(prev.max_parts, uq);
-        if (cost <= best) {
-            best = cost;
-            best_rb = rb;
-        }
-    }
-    plan->p.prev_rb = best_rb;
+    plan->pro = pro;
 }
 
 void step_plan_free(StepGemmPlan* plan) {
@@ -605,8 +541,10 @@ void step_plan_free(StepGemmPlan* plan) {
     plan->nparts_dev = nullptr;
 }
 
-int step_finalize_launch(const StepGemmPlan& consumer, int pro, cudaStream_t st) {
-    // `consumer`'s prologue fields (prev, bias / resid / x_out / ssq_out or h / I, rows) describe the work; one unit per CTA
+int step_finalize_launch(const StepGemmPlan& consumer, cudaStream_t st) {
+    // `consumer`'s finalize fields (prev, bias / resid / x_out / ssq_out or h / I, rows) describe the work; one unit per CTA
+    const int pro = consumer.pro;
+    if (pro == PRO_NONE) return 0;
     StepGemmParams p = consumer.p;
     const int rb = pro == PRO_SWIGLU ? 8 : 2;  // one load round per unit (<= 4 / <= 16 partials), every unit on its own CTA
     p.prev_rb = rb;
@@ -617,11 +555,7 @@ int step_finalize_launch(const StepGemmPlan& consumer, int pro, cudaStream_t st)
 }
 
 int step_gemm_launch(const StepGemmPlan& plan, cudaStream_t st) {
-    if (plan.pro == PRO_NONE) return plan.norm ? launch_t<PRO_NONE, 1>(plan, st) : launch_t<PRO_NONE, 0>(plan, st);
-    if (plan.pro == PRO_RESID && plan.norm) return launch_t<PRO_RESID, 1>(plan, st);
-    if (plan.pro == PRO_SWIGLU && !plan.norm) return launch_t<PRO_SWIGLU, 0>(plan, st);
-    set_error("step_gemm_launch: bad prologue %d / norm %d", plan.pro, plan.norm);
-    return 1;
+    return plan.norm ? launch_t<1>(plan, st) : launch_t<0>(plan, st);
 }
 
 }  // namespace fsb

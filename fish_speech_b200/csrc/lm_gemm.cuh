@@ -1,27 +1,31 @@
 // Step GEMM: the weight-streaming matmul of the Dual-AR decode step (llama.py:831-987 one TransformerBlock;
-// inference.py:96-181 one frame), with the element-wise work between two matmuls folded into its PROLOGUE.
+// inference.py:96-181 one frame).
 //
 //   D[i][j] = sum_k W[i][k] * X[j][k]        i = output feature (128 per tile, on the TMEM lanes)
 //                                            j = sequence slot of the batch (<= 32, the UMMA N)
 //
-// Life of one launch (one CTA = 8 warps, two CTAs per SM, the whole grid resident):
+// Life of one launch (one CTA = 6 warps + 4 normaliser warps, two CTAs per SM, the whole grid in one wave):
 //   1. The TMA producer requests the first ring-full of weight tiles at once -- before griddepcontrol.wait, i.e.
-//      while the previous kernel is still finishing: weights do not depend on anything.
-//   2. After the wait, the PROLOGUE finishes the previous GEMM, spread over all CTAs: CTA c takes (tile, row-block)
-//      units c, c+grid, ... of that GEMM's output, sums its stream-K partials IN SLOT ORDER (deterministic,
-//      independent of the batch) and applies what the reference does between the two Linears:
-//        PRO_RESID   bias, residual add, new residual stream + per-128-feature sum of squares   (llama.py:842-845)
-//        PRO_SWIGLU  silu(w1 x) * w3 x on the row-interleaved w1|w3 result                       (llama.py:979-987)
-//      then one grid-wide arrival counter says "operand complete".  The ring keeps the HBM stream busy meanwhile.
-//   3. Main loop: weights HBM -> shared memory by TMA (SWIZZLE_128B, EVICT_FIRST), operand X by TMA from L2; where X
-//      is the residual stream it is *normalised on load* -- two warps apply the reference's RMSNorm
-//      (llama.py:990-1001: round(x * rsqrt(mean(x^2) + eps)) * w, two bf16 roundings) in place in shared memory --
-//      and tcgen05.mma accumulates in TMEM.  Work is a host-built stream-K schedule: (tile, k-block) units cut into
-//      equal contiguous ranges, one per CTA.
-//   4. Each CTA stores its fp32 partials and exits: no tail holds shared memory, so the next GEMM's CTAs move in and
-//      start step 1 while this launch drains.
-// Consumers of the partials that are not GEMMs (attention after qkv, the sampler after the heads) do the same
-// slot-ordered sum in their own prologue (lm_kernels.cuh).
+//      while the previous kernels are still finishing: weights do not depend on anything.
+//   2. Main loop: weights HBM -> shared memory by TMA (SWIZZLE_128B, EVICT_FIRST), operand X by TMA from L2; where X
+//      is the residual stream it is *normalised on load* -- four warps apply the reference's RMSNorm
+//      (llama.py:990-1001: round(x * rsqrt(mean(x^2) + eps)) * w, two bf16 roundings) in place in shared memory, with
+//      the per-row sum of squares the producer of the residual stream left behind -- and tcgen05.mma accumulates in
+//      TMEM.  Work is a host-built stream-K schedule: (tile, k-block) units cut into equal contiguous ranges, one per
+//      CTA, so every SM streams the same number of weight bytes whatever the shape.
+//   3. Each CTA stores its fp32 partials and exits: no tail holds shared memory, so the next GEMM's CTAs move in and
+//      start step 1 while this launch drains and its consumer runs.
+// Whoever consumes the result finishes the GEMM: it sums the partials IN SLOT ORDER (deterministic, independent of
+// arrival order and of the batch) and applies what the reference does next:
+//   step_finalize (this file)  PRO_RESID   bias, residual add, new residual stream + per-128-feature sum of squares
+//                                          for the next normalise-on-load                          (llama.py:842-845)
+//                              PRO_SWIGLU  silu(w1 x) * w3 x on the row-interleaved w1|w3 result   (llama.py:979-987)
+//   attention (lm_kernels.cuh) bias, per-head nn.RMSNorm, RoPE, KV append for the qkv GEMM          (llama.py:891-911)
+//   sampler (lm_kernels.cuh)   bf16 logits of the two heads                                        (llama.py:447-457)
+// Measured alternatives (profiles/r02_decode_structure.md): finishing a GEMM inside its own kernel (last-arriving CTA
+// or all contributors after a per-tile arrival) or inside the consumer GEMM's prologue behind a grid-wide arrival
+// were 6.2-7.2 ms per frame against 5.5 ms for this schedule: a tail or a prologue holds the shared memory the next
+// GEMM's weight prefetch needs.
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -101,10 +105,9 @@ struct StepGemmParams {
     int l2_prefetch;        // weight k-blocks per CTA prefetched into L2 behind the ring, before the operand exists
     unsigned long long a_hint, b_hint;
     float* ws;              // out: [slot][tile][32 rows][128 features] fp32 partials
-    // ---- prologue: finish the previous GEMM (PRO != NONE) ----
+    // ---- step_finalize of the GEMM that produces this one's operand (pro != PRO_NONE) ----
     StepPartials prev;
-    int prev_rb;                  // batch rows per prologue unit (power of two)
-    unsigned* grid_bar;           // [32*9]: arrival counter (zero between launches) + 8 copies of a generation word
+    int prev_rb;                  // batch rows per finalize unit (power of two)
     const __nv_bfloat16* bias;    // PRO_RESID: [prev.n_out] or null
     const __nv_bfloat16* resid;   // PRO_RESID: [32][prev.n_out]; may alias x_out; null => no add
     __nv_bfloat16* x_out;         // PRO_RESID: [32][prev.n_out] new residual stream
@@ -116,8 +119,8 @@ struct StepGemmParams {
     const __nv_bfloat16* norm_w;  // [K]
     int x_nt;                     // tiles per row in x_ssq
     float eps;
-    // diagnostics: optional [grid][8] globaltimer stamps {start, previous grid complete, prologue done, operand
-    // complete (grid-wide), first accumulator done, end, smid, items}
+    // diagnostics: optional [grid][8] globaltimer stamps {start, previous grid complete, -, -, first accumulator done,
+    // end, normalisers ready, first tile normalised}
     unsigned long long* trace;
 };
 
@@ -135,18 +138,18 @@ struct StepGemmPlan {
 };
 
 // Operand X = act [32][K], fetched by TMA; norm_on_load: act is the un-normalised residual stream (the caller fills
-// p.x_ssq / p.norm_w / p.x_nt / p.eps). pro != PRO_NONE: link the producer of the operand with step_plan_set_prev and
-// fill the prologue fields of plan->p.
-int step_plan_init(StepGemmPlan* plan, int pro, const __nv_bfloat16* w, int n_out, int K, const __nv_bfloat16* act,
-                   bool norm_on_load, int num_ctas, int stages, float* ws, size_t ws_floats, unsigned* grid_bar);
+// p.x_ssq / p.norm_w / p.x_nt / p.eps).
+int step_plan_init(StepGemmPlan* plan, const __nv_bfloat16* w, int n_out, int K, const __nv_bfloat16* act,
+                   bool norm_on_load, int num_ctas, int stages, float* ws, size_t ws_floats);
 // the partials `plan` produces, as a consumer sees them
 StepPartials step_plan_partials(const StepGemmPlan& plan);
-// make `plan`'s prologue finish `prev` (sets p.prev and the unit size)
-void step_plan_set_prev(StepGemmPlan* plan, const StepGemmPlan& prev);
+// `plan`'s operand is the output of `prev` finished with `pro` (PRO_RESID / PRO_SWIGLU): records what
+// step_finalize_launch(plan) has to do before `plan` runs (the caller fills bias / resid / x_out / ssq_out or h / I)
+void step_plan_set_prev(StepGemmPlan* plan, int pro, const StepGemmPlan& prev);
 void step_plan_free(StepGemmPlan* plan);
 int step_gemm_launch(const StepGemmPlan& plan, cudaStream_t stream);
-// run the prologue `consumer` is set up for (step_plan_set_prev + prologue fields) as a kernel of its own
-int step_finalize_launch(const StepGemmPlan& consumer, int pro, cudaStream_t stream);
+// finish the GEMM that produces `consumer`'s operand (no-op when consumer.pro == PRO_NONE); launch it before the consumer
+int step_finalize_launch(const StepGemmPlan& consumer, cudaStream_t stream);
 int step_gemm_init();  // kernel attributes (idempotent)
 
 // Row index of the fused w1|w3 weight for SwiGLU: h feature f -> row of w1[f]; w3[f] sits 16 rows further.

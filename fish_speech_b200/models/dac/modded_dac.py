@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import threading
 from dataclasses import dataclass, field
 from typing import Iterator, Optional
@@ -114,6 +115,9 @@ class DAC:
         self.latent_dim = cfg.latent_dim
         self._keep: list[torch.Tensor] = []
         self._bufs: dict = {}
+        self._graphs: dict = {}   # (B, S, T) -> (CUDAGraph, static index buffer, static waveform) of from_indices
+        self._graph_seen: dict = {}
+        self._use_graphs = os.environ.get("FSB_CODEC_GRAPH", "1") != "0"
         self._lock = threading.RLock()
         self._rope: dict = {}
         self._sd = {k: v.detach().float() for k, v in state_dict.items()}  # folded on the device they live on
@@ -319,6 +323,9 @@ class DAC:
         """Named persistent workspace (stable device pointers keep the GEMM plan cache small)."""
         b = self._bufs.get(name)
         if b is None or b.numel() < numel or b.dtype != dtype:
+            if b is not None:
+                self._graphs.clear()  # captured graphs point into the buffer that is being replaced
+                self._graph_seen.clear()
             b = torch.empty(max(numel, 1), dtype=dtype, device=self._device)
             self._bufs[name] = b
         return b
@@ -341,18 +348,26 @@ class DAC:
             inv = 1.0 / (base ** (torch.arange(0, head_dim, 2)[: head_dim // 2].float() / head_dim))
             ang = torch.outer(torch.arange(n), inv)
             cis = torch.polar(torch.ones_like(ang), ang)
-            t = torch.stack([cis.real, cis.imag], dim=-1).to(torch.bfloat16).to(self._device)  # modded_dac.py:442-452
+            new = torch.stack([cis.real, cis.imag], dim=-1).to(torch.bfloat16).to(self._device)  # modded_dac.py:442-452
+            if t is not None:
+                self._graphs.clear()  # captured graphs point into the table that is being replaced
+                self._graph_seen.clear()
+            t = new
             self._rope[key] = t
         return t
 
-    def _transformer(self, tf: dict, x: torch.Tensor, B: int, T: int, tag: str) -> torch.Tensor:
+    def _transformer(self, tf: dict, x: torch.Tensor, B: int, T: int, tag: str, pos0: int = 0,
+                     kv_cache: Optional[list] = None, cache_len: int = 0) -> torch.Tensor:
         """WindowLimitedTransformer.forward on x = flat [B*T, D] bf16 (updated in place as the residual
-        stream); returns the final-normed tensor (a workspace view)."""
+        stream); returns the final-normed tensor (a workspace view).
+        Incremental use (DecodeStream): the T rows are positions pos0 .. pos0+T-1 of a longer sequence whose earlier
+        K/V live in `kv_cache` = per layer (K, V) buffers [B][H][cache_len][Dh]; the window attention reads them."""
         t: TfmConfig = tf["cfg"]
         D, H, Dh, I = t.dim, t.n_head, t.head_dim, t.intermediate_size
         rows = B * T
         L = self.lib
         st = _stream()
+        S = cache_len if kv_cache is not None else T
         ws = self._buf("tf_ws", rows * max(3 * H * Dh, 2 * I, D), torch.float32)
         n = self._buf("tf_n", rows * D)
         q = self._buf("tf_q", rows * H * Dh)
@@ -367,18 +382,22 @@ class DAC:
         ar = torch.arange(rows, dtype=torch.int32, device=self._device)
         torch.div(ar, T, rounding_mode="floor", out=seq)
         torch.remainder(ar, T, out=pos)
-        freqs = self._rope_table(T, Dh, t.rope_base)
+        if pos0:
+            pos += pos0
+        freqs = self._rope_table(pos0 + T, Dh, t.rope_base)
         window = t.window_size if t.window_size is not None else 0
         layers = tf["layers"]
         chk = _lib.check
         chk(L.fsb_resid_scale_norm(None, 0, None, x.data_ptr(), None, layers[0]["attn_norm"].data_ptr(), n.data_ptr(),
                                    rows, D, t.norm_eps, 0, st))
         for l, lw in enumerate(layers):
+            if kv_cache is not None:
+                kc, vc = kv_cache[l]
             chk(L.fsb_linear_f32(n.data_ptr(), rows, D, lw["wqkv"].data_ptr(), 3 * H * Dh, ws.data_ptr(), st))
             chk(L.fsb_qkv_rope(ws.data_ptr(), rows, H, H, Dh, freqs.data_ptr(), seq.data_ptr(), pos.data_ptr(),
-                               q.data_ptr(), kc.data_ptr(), vc.data_ptr(), T, st))
+                               q.data_ptr(), kc.data_ptr(), vc.data_ptr(), S, st))
             chk(L.fsb_window_attn(q.data_ptr(), kc.data_ptr(), vc.data_ptr(), seq.data_ptr(), pos.data_ptr(), rows,
-                                  H, H, Dh, T, window, att.data_ptr(), st))
+                                  H, H, Dh, S, window, att.data_ptr(), st))
             chk(L.fsb_linear_f32(att.data_ptr(), rows, H * Dh, lw["wo"].data_ptr(), D, ws.data_ptr(), st))
             chk(L.fsb_resid_scale_norm(ws.data_ptr(), D, lw["ls_attn"].data_ptr(), x.data_ptr(), x.data_ptr(),
                                        lw["ffn_norm"].data_ptr(), n.data_ptr(), rows, D, t.norm_eps, 0, st))
@@ -405,31 +424,62 @@ class DAC:
     @torch.inference_mode()
     def from_indices(self, indices: torch.Tensor) -> torch.Tensor:
         """modded_dac.py:925-927: codes [B, 1+n_codebooks, T] -> waveform [B, 1, T*frame_length] (fp32).
-        Like the reference (rvq.py:354-359) the caller's tensor is clamped in place."""
+        Like the reference (rvq.py:354-359) the caller's tensor is clamped in place.
+        The ~190 launches of one decode are captured into a CUDA graph the second time a (B, T) shape is seen and
+        replayed from then on: the layer walk below costs more host time than the GPU needs for short utterances."""
         cfg = self.cfg
         # one caller at a time per DAC object: the layers share persistent workspaces (the reference's nn.Module
         # allocates per call and may be driven from two host threads, e.g. TTSInferenceEngine + a batch encoder)
         with self._lock, torch.cuda.device(self._device):
             indices[:, 0] = torch.clamp(indices[:, 0], max=cfg.semantic_codebook_size - 1)
             indices[:, 1:] = torch.clamp(indices[:, 1:], max=cfg.codebook_size - 1)
-            idx = indices.to(device=self._device, dtype=torch.int32).contiguous()
-            B, S, T = idx.shape
-            D = cfg.latent_dim
-            z = self._buf("q_z", B * T * D)
-            _lib.check(self.lib.fsb_codebook_sum(idx.data_ptr(), self.vq_tab_ptrs.data_ptr(), self.vq_sizes.data_ptr(),
-                                                 S, B, T, D, z.data_ptr(), _stream()))
-            z = self._transformer(self.post_tfm, z, B, T, "post")
-            Tc = T
-            cur = z
-            for i, u in enumerate(self.up):
-                out = self._buf(f"up_{i}", B * Tc * u["f"] * D)
-                self._gemm(u["conv"], cur, B, Tc, D, Tc, out0=out)
-                Tc *= u["f"]
-                self._convnext_block(u["cnx"], out, B, Tc, D, f"up{i}")
-                cur = out
-            wav = self._decoder(cur, B, Tc)
-            self._idx_keepalive = idx
-            return wav.view(B, 1, -1)
+            B, S, T = indices.shape
+            key = (B, S, T)
+            hit = self._graphs.get(key)
+            if hit is not None:
+                graph, g_idx, g_wav = hit
+                g_idx.copy_(indices.reshape(-1))
+                graph.replay()
+                return g_wav.clone().view(B, 1, -1)
+            seen = self._graph_seen.get(key, 0)
+            self._graph_seen[key] = seen + 1
+            if not self._use_graphs or seen == 0 or len(self._graphs) >= 4:
+                # first sight of a shape (warms the plan cache and sizes the workspaces), or capture disabled / full
+                idx = indices.to(device=self._device, dtype=torch.int32).contiguous()
+                wav = self._from_indices_body(idx, B, S, T)
+                self._idx_keepalive = idx
+                return wav.view(B, 1, -1)
+            g_idx = torch.empty(B * S * T, dtype=torch.int32, device=self._device)
+            g_idx.copy_(indices.reshape(-1))
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):  # the LM worker thread keeps running
+                g_wav = self._from_indices_body(g_idx.view(B, S, T), B, S, T)
+            self._graphs[key] = (graph, g_idx, g_wav)
+            graph.replay()
+            return g_wav.clone().view(B, 1, -1)
+
+    def _from_indices_body(self, idx: torch.Tensor, B: int, S: int, T: int) -> torch.Tensor:
+        """idx int32 [B, S, T] (clamped) -> waveform [B, T*frame_length]: rvq.decode + Decoder.forward."""
+        D = self.cfg.latent_dim
+        z = self._buf("q_z", B * T * D)
+        _lib.check(self.lib.fsb_codebook_sum(idx.data_ptr(), self.vq_tab_ptrs.data_ptr(), self.vq_sizes.data_ptr(),
+                                             S, B, T, D, z.data_ptr(), _stream()))
+        z = self._transformer(self.post_tfm, z, B, T, "post")
+        Tc = T
+        cur = z
+        for i, u in enumerate(self.up):
+            out = self._buf(f"up_{i}", B * Tc * u["f"] * D)
+            self._gemm(u["conv"], cur, B, Tc, D, Tc, out0=out)
+            Tc *= u["f"]
+            self._convnext_block(u["cnx"], out, B, Tc, D, f"up{i}")
+            cur = out
+        return self._decoder(cur, B, Tc)
+
+    def open_decode_stream(self, batch: int = 1, max_frames: int = 4096, conv_context: int = 16) -> "DecodeStream":
+        """Incremental `from_indices`: push code frames as the LM emits them, get their samples back.
+        The codec is causal (rvq.py:395-398 asserts it), so what a frame sounds like never depends on later frames."""
+        return DecodeStream(self, batch, max_frames, conv_context)
 
     @torch.inference_mode()
     def decode(self, z: torch.Tensor) -> torch.Tensor:
@@ -559,6 +609,68 @@ class DAC:
                                               codes.data_ptr(), _stream()))
             indices_lens = torch.ceil(audio_lengths.to(self._device) / self.frame_length).long()
             return codes.long(), indices_lens
+
+
+class DecodeStream:
+    """Streaming state of one `from_indices` over a growing code sequence (one per utterance batch).
+
+    * post-transformer (8 layers, causal window 128): K/V of every layer stay in a cache; a push computes only the new
+      frames at their absolute positions (the kernels are the ones the whole-sequence path uses: row positions + cache
+      length are arguments) -- exact.
+    * upsample + decoder convolutions: causal with a finite receptive field (< 10 frames: dilated k7 convs at 4..512
+      steps per frame, ConvNeXt k7 at 2 and 4 steps per frame); the last `conv_context` frames of the transformer
+      OUTPUT are kept and re-run in front of the new frames, and only the new frames' samples are returned -- exact
+      as long as conv_context covers the receptive field (tests compare with the one-shot decode).
+    """
+
+    def __init__(self, dac: "DAC", batch: int, max_frames: int, conv_context: int):
+        self.dac, self.B, self.S, self.ctx = dac, int(batch), int(max_frames), int(conv_context)
+        t: TfmConfig = dac.post_tfm["cfg"]
+        dev = dac.device
+        n = self.B * t.n_head * self.S * t.head_dim
+        self.kv = [(torch.zeros(n, dtype=torch.bfloat16, device=dev), torch.zeros(n, dtype=torch.bfloat16, device=dev))
+                   for _ in dac.post_tfm["layers"]]
+        self.pos = 0
+        self.tail: Optional[torch.Tensor] = None  # [B, <=ctx, D] transformer output of the latest frames
+
+    @torch.inference_mode()
+    def push(self, indices: torch.Tensor) -> torch.Tensor:
+        """codes [B, 1+n_codebooks, k] of the next k frames -> waveform [B, 1, k * frame_length] (fp32)."""
+        dac, cfg = self.dac, self.dac.cfg
+        B, S_, k = indices.shape
+        if B != self.B:
+            raise ValueError(f"stream was opened for batch {self.B}, got {B}")
+        if k == 0:
+            return torch.zeros(B, 1, 0, dtype=torch.float32, device=dac.device)
+        if self.pos + k > self.S:
+            raise ValueError(f"decode stream capacity exceeded ({self.pos} + {k} > {self.S} frames)")
+        with dac._lock, torch.cuda.device(dac.device):
+            idx = indices.to(device=dac.device, dtype=torch.int32).clone()
+            idx[:, 0].clamp_(max=cfg.semantic_codebook_size - 1)  # rvq.py:354-359
+            idx[:, 1:].clamp_(max=cfg.codebook_size - 1)
+            idx = idx.contiguous()
+            D = cfg.latent_dim
+            z = dac._buf("st_z", B * k * D)
+            _lib.check(dac.lib.fsb_codebook_sum(idx.data_ptr(), dac.vq_tab_ptrs.data_ptr(), dac.vq_sizes.data_ptr(), S_, B,
+                                                k, D, z.data_ptr(), _stream()))
+            zn = dac._transformer(dac.post_tfm, z, B, k, "post", pos0=self.pos, kv_cache=self.kv, cache_len=self.S)
+            new = zn[: B * k * D].view(B, k, D)
+            seq = new if self.tail is None else torch.cat([self.tail, new], dim=1)
+            c = seq.shape[1] - k  # context frames in front of the new ones
+            Tc = seq.shape[1]
+            cur = dac._buf("st_in", B * Tc * D)
+            cur[: B * Tc * D].view(B, Tc, D).copy_(seq)
+            for i, u in enumerate(dac.up):
+                out = dac._buf(f"up_{i}", B * Tc * u["f"] * D)
+                dac._gemm(u["conv"], cur, B, Tc, D, Tc, out0=out)
+                Tc *= u["f"]
+                dac._convnext_block(u["cnx"], out, B, Tc, D, f"up{i}")
+                cur = out
+            wav = dac._decoder(cur, B, Tc).view(B, 1, -1)
+            self.tail = seq[:, -self.ctx:].clone() if self.ctx > 0 else None
+            self.pos += k
+            dac._idx_keepalive = idx
+            return wav[:, :, c * dac.frame_length:]
 
 
 class _SnakeView:

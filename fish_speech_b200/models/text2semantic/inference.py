@@ -125,15 +125,18 @@ def decode_n_tokens(
     return eng.buffer("out_tokens")[0, :, :n].clone()
 
 
-def _run_frames(eng, batch: int, max_frames: int, sp, first_frame_from_prefill: bool):
+def _run_frames(eng, batch: int, max_frames: int, sp, first_frame_from_prefill: bool, on_progress=None):
     """Decode until every sequence has emitted <|im_end|> (checked from frame index 1 on, as the
-    reference's loop does) or max_frames frames exist. Returns the kept frame count per sequence."""
+    reference's loop does) or max_frames frames exist. Returns the kept frame count per sequence.
+    `on_progress(done)`: called after every poll with the number of frames that exist on the device."""
     im_end = eng.im_end_id
     done = 1 if first_frame_from_prefill else 0
     while done < max_frames:
         step = min(_CHECK_EVERY, max_frames - done)
         eng.decode(batch, step, sp, use_graph=True)
         done += step
+        if on_progress is not None:
+            on_progress(done)
         if done < max_frames and bool(eng.buffer("finished")[:batch].all().item()):
             # every sequence has produced <|im_end|>; make sure it was at index >= 1
             toks = eng.buffer("out_tokens")[:batch, 0, :done]
@@ -210,8 +213,28 @@ def generate_batch(
         eng.prefill_reusing(list(prompts), list(range(B)), sp, do_sample=True)
     else:
         eng.prefill(list(prompts), list(range(B)), sp, do_sample=True)
-    counts = _run_frames(eng, B, max_new_tokens, sp, first_frame_from_prefill=True)
     out_tokens = eng.buffer("out_tokens")
+    frame_callback = sampling_kwargs.get("frame_callback")
+    on_progress = None
+    if frame_callback is not None:
+        # Streaming: hand the codes of finished frames to the caller while decoding goes on. What is
+        # emitted over a whole call is exactly what generate_long keeps of it, y[1:, T:-1] (inference.py:708: the last
+        # frame -- <|im_end|> or the one at the budget -- is dropped), so the newest frame is always held back.
+        emitted = [0] * B
+        im_end = eng.im_end_id
+
+        def on_progress(done: int):
+            toks = out_tokens[:B, 0, :done].cpu()
+            for b in range(B):
+                hits = (toks[b, 1:] == im_end).nonzero()
+                n = int(hits[0]) + 2 if len(hits) else done  # frames that count, the stopping one included
+                if n - 1 > emitted[b]:
+                    frame_callback(b, out_tokens[b, 1:, emitted[b]: n - 1].cpu())  # host copy: crosses threads
+                    emitted[b] = n - 1
+
+    counts = _run_frames(eng, B, max_new_tokens, sp, first_frame_from_prefill=True, on_progress=on_progress)
+    if on_progress is not None:
+        on_progress(max(counts))
     outs = []
     for b, p in enumerate(prompts):
         gen = out_tokens[b, :, : counts[b]].to(p.dtype)
@@ -264,7 +287,7 @@ def decode_to_audio(codes, codec):
 
 @dataclass
 class GenerateResponse:
-    action: Literal["sample", "next"]
+    action: Literal["sample", "next", "partial"]  # "partial": streamed codes of a chunk in progress (extension)
     codes: Optional[torch.Tensor] = None
     text: Optional[str] = None
 
@@ -422,8 +445,10 @@ def _generate_long_plan(
         yield ("response", GenerateResponse(action="next"))
 
 
-def generate_long(*, model, decode_one_token: Callable = None, **kwargs):
-    """inference.py:523-733: yields GenerateResponse("sample", codes [C, n], text) per chunk, then ("next")."""
+def generate_long(*, model, decode_one_token: Callable = None, on_partial: Optional[Callable] = None, **kwargs):
+    """inference.py:523-733: yields GenerateResponse("sample", codes [C, n], text) per chunk, then ("next").
+    `on_partial(codes [C, k])` (extension): called from inside the decode loop with the codes of the
+    frames finished since the last call; over a chunk the pieces concatenate to that chunk's "sample" codes."""
     plan = _generate_long_plan(model=model, **kwargs)
     reply = None
     while True:
@@ -433,6 +458,8 @@ def generate_long(*, model, decode_one_token: Callable = None, **kwargs):
             return
         reply = None
         if kind == "generate":
+            if on_partial is not None:
+                payload = dict(payload, frame_callback=lambda b, codes: on_partial(codes))
             reply = generate(model=model, decode_one_token=decode_one_token or decode_one_token_ar,
                              seed=_next_seed(model), **payload)
             if torch.cuda.is_available():
@@ -519,7 +546,7 @@ def serve_requests(model, input_queue: "queue.Queue", max_slots: int, frames_per
                 live += 1
                 try:
                     plan = _generate_long_plan(model=model, **{k: v for k, v in item.request.items()
-                                                               if k != "decode_one_token"})
+                                                               if k not in ("decode_one_token", "stream_frames")})
                 except Exception as e:  # pragma: no cover - argument errors surface on first send
                     item.response_queue.put(WrappedGenerateResponse(status="error", response=e))
                     live -= 1
@@ -576,10 +603,15 @@ def launch_thread_safe_queue(checkpoint_path, device, precision, compile: bool =
             item: Optional[GenerateRequest] = input_queue.get()
             if item is None:
                 break
-            kwargs = item.request
+            kwargs = dict(item.request)
             response_queue = item.response_queue
+            on_partial = None
+            if kwargs.pop("stream_frames", 0):
+                # streaming request (TTSInferenceEngine with req.streaming): codes leave the worker as frames finish
+                def on_partial(codes, q=response_queue):
+                    q.put(WrappedGenerateResponse(status="success", response=GenerateResponse(action="partial", codes=codes)))
             try:
-                for chunk in generate_long(model=model, decode_one_token=decode_one_token, **kwargs):
+                for chunk in generate_long(model=model, decode_one_token=decode_one_token, on_partial=on_partial, **kwargs):
                     response_queue.put(WrappedGenerateResponse(status="success", response=chunk))
             except Exception as e:
                 logger.error(traceback.format_exc())

@@ -213,3 +213,66 @@ def test_roundtrip_full_size_property():
         got = dac.from_indices(torch.from_numpy(z["codes"]).long().cuda()).cpu()
         s = snr_db(torch.from_numpy(z["ref_wav"]), got)
         assert s >= 30.0, f"full-size SNR vs reference {s:.1f} dB"
+
+
+@pytest.mark.parametrize("full", [False, True])
+def test_streaming_decode_equals_one_shot(tiny, full):
+    """frames pushed through DAC.open_decode_stream in uneven pieces (transformer K/V cached per layer,
+    convolutions re-run over a 16-frame tail) give the samples of the one-shot from_indices: the codec is causal
+    (rvq.py:395-398). Tiny and full (391 M, window-128 transformer) geometry."""
+    if full:
+        cfg = CO.full_config()
+        dac = build(cfg, CO.make_weights(cfg, seed=6))
+        T, pieces = 150, [8, 8, 1, 30, 64, 39]  # crosses the 128-frame attention window
+    else:
+        cfg, _, dac = tiny
+        T, pieces = 45, [3, 8, 1, 20, 13]
+    codes = rand_codes(cfg, 2, T, 77).cuda()
+    ref = dac.from_indices(codes.clone())
+    st = dac.open_decode_stream(batch=2, max_frames=256)
+    out, a = [], 0
+    for k in pieces:
+        out.append(st.push(codes[:, :, a: a + k].clone()))
+        assert out[-1].shape == (2, 1, k * dac.frame_length)
+        a += k
+    assert a == T
+    got = torch.cat(out, dim=-1)
+    assert got.shape == ref.shape
+    s = snr_db(ref.cpu(), got.cpu())
+    print(f"streamed vs one-shot decode ({'full' if full else 'tiny'}): SNR {s:.1f} dB, bitwise equal: {torch.equal(got, ref)}")
+    assert s >= 80.0, f"streamed decode differs from the one-shot decode: SNR {s:.1f} dB"
+    with pytest.raises(ValueError):
+        st.push(codes[:, :, :200].clone())  # over the stream's capacity
+
+
+def test_bulk_encode_with_the_real_codec(tiny, tmp_path):
+    """SURVEY §8(f).4 on the GPU: fish_speech_b200.bulk_encode.encode_files (extract_vq.py's contract: one `<file>.npy` per
+    clip) with the CUDA codec on ragged clips, padded into batches: every file's codes equal `DAC.encode` of that clip
+    alone (the encoder is causal and batch-invariant, so padding neighbours cannot change a clip's codes)."""
+    import wave
+
+    from fish_speech_b200 import bulk_encode as BE
+
+    cfg, _, dac = tiny
+    g = torch.Generator().manual_seed(3)
+    files, clips = [], []
+    for i, n in enumerate([2048 * 5 + 17, 2048 * 9, 2048 * 2 + 1000, 2048 * 9 + 1, 2048 * 7]):
+        x = (0.1 * torch.randn(n, generator=g)).clamp(-1, 1)
+        pcm = (x * 32767).round().to(torch.int16)
+        f = tmp_path / f"clip{i}.wav"
+        with wave.open(str(f), "wb") as wf:
+            wf.setnchannels(1)
+            wf.setsampwidth(2)
+            wf.setframerate(cfg.sample_rate)
+            wf.writeframes(pcm.numpy().tobytes())
+        files.append(f)
+        clips.append(pcm.float() / 32768.0)
+    done, seconds = BE.encode_files(files, dac, batch_size=3)
+    assert done == 5 and abs(seconds - sum(len(c) for c in clips) / cfg.sample_rate) < 1e-3
+    for f, x in zip(files, clips):
+        got = np.load(f.with_suffix(".npy"))
+        solo, lens = dac.encode(x.view(1, 1, -1).cuda(), torch.tensor([len(x)]).cuda())
+        n = int(lens[0])
+        assert got.shape == (cfg.n_codebooks + 1, n) and n == -(-len(x) // 2048)
+        assert np.array_equal(got, solo[0, :, :n].cpu().numpy()), f"{f.name}: batched codes differ from the solo encode"
+    assert BE.pending_files(files, 0, 1) == []  # finished files are skipped on a re-run (extract_vq.py:161-166)

@@ -85,6 +85,81 @@ def test_tts_engine_streaming_and_errors():
     q.put(None)
 
 
+class _FakeStream:
+    """Incremental decoder stand-in: sample value = absolute frame index, so ordering / completeness show in the audio."""
+
+    def __init__(self):
+        self.pos = 0
+
+    def push(self, codes):
+        k = codes.shape[-1]
+        out = torch.arange(self.pos, self.pos + k, dtype=torch.float32).repeat_interleave(2048).view(1, 1, -1)
+        self.pos += k
+        return out
+
+
+def test_tts_engine_streams_partial_codes():
+    """Streaming request: the worker announces finished frames ("partial") while the chunk is still being generated;
+    every piece is decoded incrementally and handed out at once, the chunk's "sample" only closes it (frames the worker
+    did not announce are decoded then), a new chunk starts a new codec stream, and `final` is the concatenation."""
+    import threading
+
+    def serve(q):
+        item = q.get()
+        assert item.request["stream_frames"] == 8
+        put = lambda a, n=0: item.response_queue.put(inf.WrappedGenerateResponse(
+            status="success", response=inf.GenerateResponse(action=a, codes=torch.zeros(10, n, dtype=torch.long) if n else None)))
+        put("partial", 8)
+        put("partial", 5)
+        put("sample", 15)   # 2 frames were never announced
+        put("partial", 3)
+        put("sample", 3)
+        put("sample", 4)    # a chunk without partials: one-shot decode
+        put("next")
+
+    q = queue.Queue()
+    threading.Thread(target=serve, args=(q,), daemon=True).start()
+    dac = _fake_dac()
+    dac.open_decode_stream = lambda batch=1, max_frames=4096: _FakeStream()
+    eng = TTSInferenceEngine(q, dac, torch.bfloat16, compile=False)
+    res = list(eng.inference(ServeTTSRequest(text="hi", streaming=True)))
+    assert [r.code for r in res] == ["header"] + ["segment"] * 5 + ["final"]
+    seg = [r.audio[1] for r in res[1:-1]]
+    assert [len(x) // 2048 for x in seg] == [8, 5, 2, 3, 4]
+    first_chunk = np.concatenate(seg[:3])
+    assert np.array_equal(first_chunk[::2048], np.arange(15, dtype=np.float32))  # frames in order, none lost or repeated
+    assert np.array_equal(seg[3][::2048], np.arange(3, dtype=np.float32))          # the next chunk restarts the stream
+    assert np.allclose(seg[4], 0.25)                                               # one-shot from_indices
+    assert np.array_equal(res[-1].audio[1], np.concatenate(seg))
+    assert eng.last_first_audio_s is not None and eng.last_first_audio_s >= 0
+
+
+def test_worker_forwards_partial_codes(monkeypatch):
+    """launch_thread_safe_queue: `stream_frames` in a request makes the worker forward generate_long's on_partial
+    calls as "partial" responses, in order, before the chunk's "sample"."""
+
+    def fake_generate_long(*, model, decode_one_token, text, on_partial=None, **kw):
+        assert "stream_frames" not in kw
+        if on_partial is not None:
+            on_partial(torch.ones(10, 8, dtype=torch.long))
+            on_partial(torch.ones(10, 2, dtype=torch.long))
+        yield inf.GenerateResponse(action="sample", codes=torch.ones(10, 10, dtype=torch.long), text=text)
+        yield inf.GenerateResponse(action="next")
+
+    monkeypatch.setattr(inf, "init_model", lambda *a, **k: (_FakeModel(), inf.decode_one_token_ar))
+    monkeypatch.setattr(inf, "generate_long", fake_generate_long)
+    q = inf.launch_thread_safe_queue("ckpt", "cpu", torch.bfloat16)
+    rq = queue.Queue()
+    q.put(inf.GenerateRequest(request=dict(text="hello", stream_frames=8), response_queue=rq))
+    got = [rq.get(timeout=10) for _ in range(4)]
+    assert [g.response.action for g in got] == ["partial", "partial", "sample", "next"]
+    assert [g.response.codes.shape[-1] for g in got[:3]] == [8, 2, 10]
+    q.put(inf.GenerateRequest(request=dict(text="plain"), response_queue=rq))
+    got = [rq.get(timeout=10) for _ in range(2)]
+    assert [g.response.action for g in got] == ["sample", "next"]
+    q.put(None)
+
+
 def test_wav_chunk_header_is_riff():
     from fish_speech_b200.inference_engine.utils import wav_chunk_header
 
@@ -414,3 +489,93 @@ def test_continuous_batcher_rejects_bad_requests_up_front():
             b.submit(SlotRequest(**{**ok, **bad}))
     b.submit(SlotRequest(**ok))
     assert len(b.waiting) == 1
+
+
+class _ByteTokenizer:
+    """Stand-in for FishTokenizer (fish_speech/tokenizer.py): bytes are ids 0..255, the handful of special tokens the
+    prompt builder emits get ids from 256, semantic tokens start at 1000."""
+
+    semantic_begin_id, semantic_end_id = 1000, 1000 + 4095
+
+    def __init__(self):
+        import re
+
+        self.special = {}
+        self._re = re.compile(r"(<\|[^|]+\|>)")
+
+    def get_token_id(self, token):
+        return self.special.setdefault(token, 256 + len(self.special))
+
+    def encode(self, text, add_special_tokens=False, **kw):
+        ids = []
+        for piece in self._re.split(text):
+            if not piece:
+                continue
+            ids += [self.get_token_id(piece)] if self._re.fullmatch(piece) else list(piece.encode("utf-8"))
+        return ids
+
+
+def test_generate_long_plan_builds_growing_prompts_with_the_reference_frontend():
+    """The REAL body of the generate_long plan (inference.py:523-733) on CPU: the reference's own prompt builder
+    (fish_speech.content_sequence / conversation from /root/reference) with a byte-level tokenizer, a driver that answers
+    every `generate` with a made-up continuation. Checks what the CUDA side relies on: every chunk's prompt EXTENDS the
+    previous chunk's prompt (prefix K/V reuse), the reference clip enters as semantic rows, each chunk
+    yields y[1:, T:-1] (the last frame is dropped, :708) and the stream ends with "next"."""
+    import sys
+    from pathlib import Path
+
+    ref = Path("/root/reference")
+    if not (ref / "fish_speech" / "conversation.py").exists():
+        pytest.skip("the reference checkout (CPU-side prompt builder) is not available")
+    if str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+
+    class Model:
+        class config:
+            max_seq_len, num_codebooks = 8192, 10
+
+        tokenizer = _ByteTokenizer()
+
+    tok = Model.tokenizer
+    ref_codes = torch.arange(10 * 6).view(10, 6) % 1024
+    text = "<|speaker:0|>" + "first sentence of the request. " * 3 + "<|speaker:1|>" + "and a reply that is long enough. " * 3
+    plan = inf._generate_long_plan(model=Model, device="cpu", text=text, chunk_length=100, max_new_tokens=64,
+                                   temperature=0.8, top_p=0.8, top_k=30, prompt_text=["reference words"],
+                                   prompt_tokens=[ref_codes])
+    prompts, responses, reply, fake_frames = [], [], None, 0
+    while True:
+        try:
+            kind, payload = plan.send(reply)
+        except StopIteration:
+            break
+        reply = None
+        if kind == "response":
+            responses.append(payload)
+            continue
+        p = payload["prompt"]
+        assert payload["reuse_prefix"] is True and payload["max_new_tokens"] == 64
+        assert p.shape[0] == 11 and p.dtype in (torch.int32, torch.int64)
+        prompts.append(p.clone())
+        fake_frames += 1
+        n = 4 + fake_frames  # frames this "generate" produced; the last one is <|im_end|>
+        gen = torch.zeros(11, n, dtype=p.dtype)
+        gen[0] = tok.semantic_begin_id + 7 * fake_frames
+        gen[1:] = (torch.arange(10).view(10, 1) + fake_frames) % 1024
+        gen[0, -1] = tok.get_token_id("<|im_end|>")
+        reply = torch.cat([p, gen], dim=1)
+    assert len(prompts) >= 2, "the text must split into several chunks"
+    # the reference clip: semantic ids on row 0, its codes on rows 1..10
+    first = prompts[0]
+    sem = (first[0] >= tok.semantic_begin_id) & (first[0] <= tok.semantic_end_id)
+    assert int(sem.sum()) == 6 and torch.equal(first[1:, sem], ref_codes.to(first.dtype))
+    assert torch.equal(first[0, sem], (ref_codes[0] + tok.semantic_begin_id).to(first.dtype))
+    assert int(first[1:, ~sem].abs().sum()) == 0  # text rows carry no codes
+    for a, b in zip(prompts, prompts[1:]):
+        assert b.shape[1] > a.shape[1] and torch.equal(b[:, : a.shape[1]], a), "a chunk's prompt must extend the previous one"
+    # previous generations come back as semantic rows right after the previous prompt
+    k = prompts[0].shape[1]
+    assert torch.equal(prompts[1][1:, k: k + 4], ((torch.arange(10).view(10, 1) + 1) % 1024).expand(10, 4).to(prompts[1].dtype))
+    kinds = [r.action for r in responses]
+    assert kinds == ["sample"] * len(prompts) + ["next"]
+    for i, r in enumerate(responses[:-1]):
+        assert r.codes.shape == (10, 4 + i) and torch.equal(r.codes[:, 0], (torch.arange(10) + i + 1) % 1024)

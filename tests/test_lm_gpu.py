@@ -265,3 +265,74 @@ def test_large_kv_capacity_small_context():
     ref = O.generate(O.setup(ref_cfg, w), p, 6, temperature=0.7, top_p=0.7, top_k=1, traces=traces, noise=False)
     got = _gen(build_model(cfg, w), p, 6, temperature=0.7, top_p=0.7, top_k=1)
     assert assert_tokens_match(got, ref, traces, ref_cfg, 20, "kv capacity 32768") >= 4
+
+
+def test_frame_callback_streams_exactly_the_kept_codes():
+    """generate(frame_callback=...) hands out the codes of finished frames while decoding continues; the pieces
+    concatenate to what generate_long keeps of the call, y[1:, T:-1] (inference.py:708), for a budget-limited run and
+    for one that stops on <|im_end|>."""
+    from fish_speech_b200.models.text2semantic.inference import generate
+
+    cfg = O.tiny_config()
+    w = O.make_weights(cfg, seed=61, head_gain=8.0)
+    p = make_prompt(cfg, 61, 10)
+    model = build_model(cfg, w, debug=False)
+    for tweak in (False, True):
+        if tweak:  # make <|im_end|> win at generated frame 11
+            free = generate(model=model, prompt=p.cuda(), max_new_tokens=20, temperature=0.7, top_p=0.7, top_k=1).cpu()
+            w2 = dict(w)
+            w2["embeddings.weight"] = w["embeddings.weight"].clone()
+            w2["embeddings.weight"][cfg.im_end_id] = (w["embeddings.weight"][int(free[0, 10 + 11])].float() * 1.5).bfloat16()
+            model = build_model(cfg, w2, debug=False)
+        pieces = []
+        y = generate(model=model, prompt=p.cuda(), max_new_tokens=20, temperature=0.7, top_p=0.7, top_k=1,
+                     frame_callback=lambda b, codes: pieces.append(codes.clone()))
+        kept = y[1:, 10:-1].cpu()
+        got = torch.cat(pieces, dim=1) if pieces else kept[:, :0]
+        assert len(pieces) >= 2 and all(c.device.type == "cpu" for c in pieces)
+        assert torch.equal(got.to(kept.dtype), kept), (got.shape, kept.shape)
+        if tweak:
+            assert y[0, -1].item() == cfg.im_end_id and y.shape[1] < 30
+
+
+def _rolled_layers(cfg: O.LMConfig, seed: int, head_gain: float) -> dict:
+    """Full-size synthetic weights without drawing 4.5 G random numbers: layer l of a stack is layer 0's tensors rolled by
+    l rows (every layer distinct, so a mixed-up layer index changes the result), embeddings / heads drawn once."""
+    one = O.LMConfig(**{**cfg.__dict__, "n_layer": 1, "n_fast_layer": 1})
+    w = O.make_weights(one, seed=seed, head_gain=head_gain)
+    for stack, n in (("layers", cfg.n_layer), ("fast_layers", cfg.n_fast_layer)):
+        base = {k: v for k, v in w.items() if k.startswith(f"{stack}.0.")}
+        for l in range(1, n):
+            for k, v in base.items():
+                w[k.replace(f"{stack}.0.", f"{stack}.{l}.")] = torch.roll(v, shifts=l, dims=0) if v.ndim == 2 else v
+    return w
+
+
+def test_full_s2pro_geometry_batch32():
+    """The real size: 36 + 4 layers at S2-Pro dimensions (dim 2560, 32/8 heads x 128, I 9728, 10 x 4096 codes, the 4097
+    selectable head rows), batch 32 -- the benchmark's configuration. Sequences 0, 13 and 31 of the batch are checked
+    against the CPU oracle run on each of them alone: token ids and codes identical up to the first decision the oracle
+    itself took on a bf16 near-tie (random weights, 4096-way decisions). Vocabulary reduced to keep the CPU side short."""
+    from fish_speech_b200.models.text2semantic.inference import generate_batch
+
+    cfg = O.LMConfig(vocab_size=8192, max_seq_len=128, semantic_begin_id=4000, semantic_end_id=8095, im_end_id=3999)
+    w = _rolled_layers(cfg, seed=52, head_gain=6.0)
+    prompts = [make_prompt(cfg, 500 + i, 20 + (i % 5)) for i in range(32)]
+    model = build_model(cfg, w, max_batch=32, debug=False)
+    outs = generate_batch(model=model, prompts=[p.cuda() for p in prompts], max_new_tokens=3, temperature=0.7, top_p=0.7,
+                          top_k=1)
+    st = O.setup(cfg, w)
+    verified = 0
+    for i in (0, 13, 31):
+        traces = []
+        ref = O.generate(O.setup(cfg, w) if i else st, prompts[i], 3, temperature=0.7, top_p=0.7, top_k=1, traces=traces,
+                         stop_on_im_end=False, noise=False)
+        T = prompts[i].shape[1]
+        frames = assert_tokens_match(outs[i][:, : ref.shape[1]], ref, traces, cfg, T, f"full size, sequence {i}")
+        got, want = outs[i].cpu().to(torch.int32), ref.to(torch.int32)
+        f = T + frames
+        verified += frames * cfg.num_codebooks
+        if f < want.shape[1]:  # decisions of the frame with the near-tie that precede it
+            r = int((got[:, f] != want[:, f]).nonzero()[0])
+            verified += max(0, r - 1)
+    assert verified >= 20, f"only {verified} of 90 decisions verified before near-ties"
