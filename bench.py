@@ -527,10 +527,10 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "stages": ["lm_prefill", "lm_decode", "codec_decode"],
-                       "sampling": "greedy top_k=1 T=0.7 top_p=0.7",
+                       "utterances": args.batch * world, "sampling": "greedy top_k=1 T=0.7 top_p=0.7",
                        "step": "bounded sample of the workload, see cpu_baseline.sample",
-                       "t_prefill_s": r["t_prefill_s"], "t_frame_s": r["t_frame_s"], "t_codec_s": r["t_codec_s"],
-                       "frames_per_step": r["frames_per_step"], "codec_frames_per_step": r["codec_frames_per_step"]},
+                       "measured": {k: r[k] for k in ("t_prefill_s", "t_frame_s", "t_codec_s", "frames_per_step",
+                                                      "codec_frames_per_step")}},
             "cpu_baseline": cb,
             "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -552,7 +552,19 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg = s2pro_cfg()
     B, NF = args.batch, args.frames
-    weights = synthetic.lm_state_dict(cfg, dev)
+    # N > 1: rank 0 synthesises the checkpoint, the other ranks receive it over NCCL (NVLink) -- the start-up path of a
+    # multi-GPU deployment; outside the timed region
+    weights = synthetic.lm_state_dict(cfg, dev) if rank == 0 else None
+    weights_from = "synthesised on the device"
+    if world > 1:
+        from fish_speech_b200.parallel import broadcast_state_dict
+
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        weights = broadcast_state_dict(weights, 0, dev)
+        torch.cuda.synchronize()
+        nbytes = sum(v.numel() * v.element_size() for v in weights.values())
+        weights_from = f"rank 0 -> NCCL broadcast, {nbytes / 1e9:.2f} GB in {time.perf_counter() - t0:.2f} s"
     # fixed-length workload ("<|im_end|> bias set to -inf"): a zero head row gives
     # <|im_end|> the logit 0, which never beats the best of 4096 random semantic logits
     weights["embeddings.weight"][S2PRO_IM_END_ID] = 0
@@ -687,7 +699,7 @@ def main():
                 "ms_per_frame": frame_ms, "ms_per_decode_frame": decode_ms, "prefill_ms": prefill_ms,
                 "codec_ms": codec["ms"] if codec else None, "sampling": "greedy top_k=1 T=0.7 top_p=0.7",
                 "l2_note": "inputs larger than L2: 9.1 GB of weights streamed per frame (126 MB L2)",
-                "parallelism": f"replica x{world}, utts[rank::world]",
+                "parallelism": f"replica x{world}, utts[rank::world]", "weights": weights_from,
                 "step_hbm_frac": frame_bytes / (frame_ms / 1e3) / 1e9 / pk["hbm_gbs"],
             },
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -696,8 +708,9 @@ def main():
             "roofline": {
                 "bound": "hbm", "achieved": dec_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": dec_gbs / pk["hbm_gbs"], "traffic": ncu_traffic(), "peak_kind": pk_kind,
-                "kernel": "step_gemm_kernel (tcgen05 + TMA weight streaming, stream-K with in-kernel fix-up and fused "
-                          "epilogues), in-frame: bytes of one decode frame (weights + KV) / device time of one frame",
+                "kernel": "step_gemm_kernel (tcgen05 + TMA weight streaming, host-scheduled stream-K, RMSNorm applied on "
+                          "operand load; partials finished by the consuming kernels), in-frame: bytes of one decode frame "
+                          "(weights + KV) / device time of one frame",
                 "bytes_per_launch": dec_bytes / nl.value, "launches_per_frame": nl.value,
                 "avg_launch_us": decode_ms * 1e3 / nl.value, "frame_bytes": dec_bytes, "frame_ms": decode_ms,
                 "replay": {"achieved": gemm_gbs, "frac": gemm_gbs / pk["hbm_gbs"], "bytes_per_launch": wb.value / nl.value,

@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
     L.fsb_lm_buffer.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.fsb_lm_set_sampler_noise.argtypes = [vp, vp, i32, i32]
     L.fsb_lm_copy_kv.argtypes = [vp, i32, i32, i32, vp]
+    L.fsb_lm_trace_frame.argtypes = [vp, i32, C.POINTER(Sampling), vp, i32, vp]
     L.fsb_lm_trace_step_gemms.argtypes = [vp, vp, i32, C.POINTER(i32), vp]
     L.fsb_lm_bench_gemms.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(i32), vp]
     f32p, i32p, ll = C.c_void_p, C.POINTER(C.c_int), C.c_longlong
@@ -95,6 +96,7 @@ def lib() -> C.CDLL:
     L.fsb_vq_encode.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
     L.fsb_resid_scale_norm.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, C.c_float, i32, vp]
     L.fsb_qkv_rope.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]
+    L.fsb_op_attn_score_chunk.argtypes = [i32]
     L.fsb_window_attn.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
     L.fsb_swiglu_f32.argtypes = [vp, i32, i32, vp, vp]
     L.fsb_op_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]

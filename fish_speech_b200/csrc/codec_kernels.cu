@@ -477,6 +477,11 @@ int fsb_window_attn(const void* d_q, const void* d_k, const void* d_v, const int
     return launch_attn(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int fsb_op_attn_score_chunk(int positions) {
+    attn_set_score_chunk(positions);
+    return 0;
+}
+
 int fsb_swiglu_f32(const float* d_y, int rows, int I, void* d_h, void* stream) {
     SwigluArgs a{};
     a.y = d_y;

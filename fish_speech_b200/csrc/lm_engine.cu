@@ -101,6 +101,8 @@ struct fsb_lm {
     const float* noise_u = nullptr;
     int noise_draws = 0, noise_ld = 0;
     int ctx_lcap = 0;  // score-buffer bound for the slow attention (0 = capacity)
+    unsigned long long* trace_base = nullptr;  // fsb_lm_trace_frame: per-CTA stamps of every step GEMM of one frame
+    int trace_next = 0, trace_max = 0;
     int graph_lcap = -1;
     // decode graph cache
     cudaGraphExec_t graph_exec = nullptr;
@@ -204,6 +206,8 @@ int run_stack_decode(fsb_lm* h, Stack& s, int rows, const int* row_seq, const in
         StepGemmPlan q = plan;
         q.p.rows = rows;
         FSB_TRY(step_finalize_launch(q, st));
+        if (h->trace_base && h->trace_next < h->trace_max && q.grid.x <= 512)
+            q.p.trace = h->trace_base + static_cast<size_t>(h->trace_next++) * 8 * 512;
         return step_gemm_launch(q, st);
     };
     for (int l = 0; l < s.nl; ++l) {
@@ -311,6 +315,8 @@ int run_frame_tail(fsb_lm* h, int rows, const int* row_slot, bool use_ras, const
         StepGemmPlan q = plan;
         q.p.rows = rows;
         FSB_TRY(step_finalize_launch(q, st));
+        if (h->trace_base && h->trace_next < h->trace_max && q.grid.x <= 512)
+            q.p.trace = h->trace_base + static_cast<size_t>(h->trace_next++) * 8 * 512;
         return step_gemm_launch(q, st);
     };
     auto sample_args = [&](int n, const StepGemmPlan& head) {
@@ -815,6 +821,23 @@ int fsb_lm_copy_kv(fsb_lm* h, int src_slot, int dst_slot, int n_pos, void* strea
     FSB_TRY(launch_kv_copy(s.kcache, s.nl, h->cfg.max_batch, s.Hkv, s.S, s.Dh, src_slot, dst_slot, n_pos, st));
     FSB_TRY(launch_kv_copy(s.vcache, s.nl, h->cfg.max_batch, s.Hkv, s.S, s.Dh, src_slot, dst_slot, n_pos, st));
     return 0;
+}
+
+int fsb_lm_trace_frame(fsb_lm* h, int batch, const fsb_sampling* sp, unsigned long long* d_trace, int max_launches,
+                       void* stream) {
+    // Diagnostic: ONE decode frame, eager launches (same kernels, same programmatic dependent launch as the graph),
+    // every step GEMM recording its per-CTA stamps in launch order: the in-frame timeline at GEMM granularity.
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    FSB_CHECK(h != nullptr && sp != nullptr && d_trace != nullptr, "trace_frame: null argument");
+    FSB_CHECK(batch >= 1 && batch <= h->cfg.max_batch, "trace_frame: batch=%d", batch);
+    h->trace_base = d_trace;
+    h->trace_next = 0;
+    h->trace_max = max_launches;
+    const int rc = decode_one_frame(h, batch, *sp, st);
+    const int n = h->trace_next;
+    h->trace_base = nullptr;
+    h->trace_next = h->trace_max = 0;
+    return rc != 0 ? -1 : n;
 }
 
 int fsb_lm_trace_step_gemms(fsb_lm* h, unsigned long long* d_trace, int max_launches, int* grid_out, void* stream) {

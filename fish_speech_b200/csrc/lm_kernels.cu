@@ -281,6 +281,162 @@ __global__ void qkv_prep_kernel(QkvPrepArgs a) {
 constexpr int kAttnThreads = 256;
 constexpr int kAttnWarps = kAttnThreads / 32;
 
+// Softmax(q k^T) v of one query token against positions [0, L) of one KV group: all G query heads of the group at once.
+// The score buffer holds `lcap` positions per head (a multiple of 32).  A context that fits is scored once; a longer
+// one is walked in chunks of lcap three times -- maximum, sum of exponentials, weighted values -- recomputing the
+// scores each time.  Chunk boundaries are multiples of 32, so every lane and every warp accumulates exactly the
+// sequence of terms it would in one pass: the result is bit-identical to the unchunked kernel, whatever lcap is.
+template <int DH, int G>
+__device__ __forceinline__ void attend(const float* qs, float* sc, float* red, const __nv_bfloat16* kc,
+                                       const __nv_bfloat16* vc, int L, int lcap, float scale, int bf16_math,
+                                       __nv_bfloat16* out) {
+    static_assert(G <= kAttnWarps, "one warp per query head in the softmax");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int LPR = DH / 8;    // lanes per cache row (16-byte loads)
+    constexpr int RPW = 32 / LPR;  // rows per warp iteration
+    constexpr int UNR = 4;         // independent 16-byte loads in flight per lane
+    constexpr int DPL = DH / 32;   // value dims per lane
+    const int sub = lane / LPR, li = lane % LPR;
+    float qr[G][8];
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qr[gg][e] = qs[gg * DH + li * 8 + e];
+
+    auto scores = [&](int c0, int n) {  // sc[gg][p - c0] for p in [c0, c0 + n)
+        const __nv_bfloat16* kcc = kc + static_cast<size_t>(c0) * DH;
+        for (int pb = warp * RPW * UNR; pb < n; pb += kAttnWarps * RPW * UNR) {
+            uint4 u[UNR];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int p = pb + j * RPW + sub;
+                u[j] = make_uint4(0, 0, 0, 0);
+                if (p < n) u[j] = *reinterpret_cast<const uint4*>(kcc + static_cast<size_t>(p) * DH + li * 8);
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int p = pb + j * RPW + sub;
+                const bool ok = p < n;
+                const float kf[8] = {bf_lo(u[j].x), bf_hi(u[j].x), bf_lo(u[j].y), bf_hi(u[j].y),
+                                     bf_lo(u[j].z), bf_hi(u[j].z), bf_lo(u[j].w), bf_hi(u[j].w)};
+#pragma unroll
+                for (int gg = 0; gg < G; ++gg) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) d += qr[gg][e] * kf[e];
+#pragma unroll
+                    for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                    if (ok && li == 0) sc[gg * lcap + p] = bf16_math ? rbf(rbf(d) * scale) : d * scale;
+                }
+            }
+        }
+        __syncthreads();
+    };
+
+    const bool one = L <= lcap;
+    float m = -INFINITY, z = 0.f;  // of head `warp` (warps < G)
+    if (one) {
+        scores(0, L);
+        if (warp < G) {
+            float* s = sc + warp * lcap;
+            for (int p = lane; p < L; p += 32) m = fmaxf(m, s[p]);
+            m = warp_max(m);
+            for (int p = lane; p < L; p += 32) {
+                const float e = expf(s[p] - m);
+                s[p] = e;
+                z += e;
+            }
+            z = warp_sum(z);
+            for (int p = lane; p < L; p += 32) {
+                const float pr = s[p] / z;
+                s[p] = bf16_math ? rbf(pr) : pr;
+            }
+        }
+        __syncthreads();
+    } else {
+        for (int c0 = 0; c0 < L; c0 += lcap) {
+            const int n = min(lcap, L - c0);
+            scores(c0, n);
+            if (warp < G)
+                for (int p = lane; p < n; p += 32) m = fmaxf(m, sc[warp * lcap + p]);
+            __syncthreads();
+        }
+        m = warp_max(m);
+        for (int c0 = 0; c0 < L; c0 += lcap) {
+            const int n = min(lcap, L - c0);
+            scores(c0, n);
+            if (warp < G)
+                for (int p = lane; p < n; p += 32) z += expf(sc[warp * lcap + p] - m);
+            __syncthreads();
+        }
+        z = warp_sum(z);
+    }
+
+    float acc[G][DPL];
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg)
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) acc[gg][e] = 0.f;
+    for (int c0 = 0; c0 < L; c0 += lcap) {
+        const int n = min(lcap, L - c0);
+        if (!one) {
+            scores(c0, n);
+            if (warp < G) {
+                float* s = sc + warp * lcap;
+                for (int p = lane; p < n; p += 32) {
+                    const float pr = expf(s[p] - m) / z;
+                    s[p] = bf16_math ? rbf(pr) : pr;
+                }
+            }
+            __syncthreads();
+        }
+        const __nv_bfloat16* vcc = vc + static_cast<size_t>(c0) * DH;
+        for (int pb = warp; pb < n; pb += kAttnWarps * UNR) {
+            float vf[UNR][DPL];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int p = pb + j * kAttnWarps;
+#pragma unroll
+                for (int e = 0; e < DPL; ++e) vf[j][e] = 0.f;
+                if (p < n) {
+                    if (DPL == 4) {
+                        const uint2 u2 = *reinterpret_cast<const uint2*>(vcc + static_cast<size_t>(p) * DH + lane * 4);
+                        vf[j][0] = bf_lo(u2.x); vf[j][1] = bf_hi(u2.x); vf[j][2 % DPL] = bf_lo(u2.y); vf[j][3 % DPL] = bf_hi(u2.y);
+                    } else {
+                        const uint32_t u1 = *reinterpret_cast<const uint32_t*>(vcc + static_cast<size_t>(p) * DH + lane * 2);
+                        vf[j][0] = bf_lo(u1); vf[j][1] = bf_hi(u1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+                const int p = pb + j * kAttnWarps;
+                if (p < n) {
+#pragma unroll
+                    for (int gg = 0; gg < G; ++gg) {
+                        const float w = sc[gg * lcap + p];
+#pragma unroll
+                        for (int e = 0; e < DPL; ++e) acc[gg][e] += w * vf[j][e];
+                    }
+                }
+            }
+        }
+        if (!one) __syncthreads();  // the next chunk overwrites the scores
+    }
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg)
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) red[(warp * G + gg) * DH + lane * DPL + e] = acc[gg][e];
+    __syncthreads();
+    for (int e = threadIdx.x; e < G * DH; e += kAttnThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kAttnWarps; ++w) s += red[w * G * DH + e];
+        out[e] = f2bf(s);
+    }
+}
+
+
 template <int DH, int G>
 __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnArgs a, float scale, int lcap) {
     pdl_launch_dependents();
@@ -289,7 +445,6 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnArgs a, float sc
     float* qs = sm;                      // [G][DH]
     float* sc = qs + G * DH;             // [G][lcap]
     float* red = sc + G * lcap;          // [kAttnWarps][G][DH]
-    __shared__ float red2[33];
     const int row = blockIdx.y, g = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = a.row_seq[row], pos = min(a.row_pos[row], a.S - 1);  // a position past the cache reads its last row
@@ -310,113 +465,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnArgs a, float sc
     }
     __syncthreads();
 
-    // ---- scores ----
-    constexpr int LPR = DH / 8;    // lanes per cache row (16-byte loads)
-    constexpr int RPW = 32 / LPR;  // rows per warp iteration
-    const int sub = lane / LPR, li = lane % LPR;
-    float qr[G][8];
-#pragma unroll
-    for (int gg = 0; gg < G; ++gg)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) qr[gg][e] = qs[gg * DH + li * 8 + e];
-    constexpr int UNR = 4;  // independent 16-byte loads in flight per lane
-    for (int pb = warp * RPW * UNR; pb < L; pb += kAttnWarps * RPW * UNR) {
-        uint4 u[UNR];
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-            const int p = pb + j * RPW + sub;
-            u[j] = make_uint4(0, 0, 0, 0);
-            if (p < L) u[j] = *reinterpret_cast<const uint4*>(kc + static_cast<size_t>(p) * DH + li * 8);
-        }
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-            const int p = pb + j * RPW + sub;
-            const bool ok = p < L;
-            const float kf[8] = {bf_lo(u[j].x), bf_hi(u[j].x), bf_lo(u[j].y), bf_hi(u[j].y),
-                                 bf_lo(u[j].z), bf_hi(u[j].z), bf_lo(u[j].w), bf_hi(u[j].w)};
-#pragma unroll
-            for (int gg = 0; gg < G; ++gg) {
-                float d = 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) d += qr[gg][e] * kf[e];
-#pragma unroll
-                for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                if (ok && li == 0) sc[gg * lcap + p] = a.bf16_math ? rbf(rbf(d) * scale) : d * scale;
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- softmax (warp per head) ----
-    for (int gg = warp; gg < G; gg += kAttnWarps) {
-        float* s = sc + gg * lcap;
-        float m = -INFINITY;
-        for (int p = lane; p < L; p += 32) m = fmaxf(m, s[p]);
-        m = warp_max(m);
-        float z = 0.f;
-        for (int p = lane; p < L; p += 32) {
-            const float e = expf(s[p] - m);
-            s[p] = e;
-            z += e;
-        }
-        z = warp_sum(z);
-        for (int p = lane; p < L; p += 32) {
-            const float pr = s[p] / z;
-            s[p] = a.bf16_math ? rbf(pr) : pr;
-        }
-    }
-    __syncthreads();
-    (void)red2;
-
-    // ---- P.V ----
-    constexpr int DPL = DH / 32;  // dims per lane
-    float acc[G][DPL];
-#pragma unroll
-    for (int gg = 0; gg < G; ++gg)
-#pragma unroll
-        for (int e = 0; e < DPL; ++e) acc[gg][e] = 0.f;
-    for (int pb = warp; pb < L; pb += kAttnWarps * UNR) {
-        float vf[UNR][DPL];
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-            const int p = pb + j * kAttnWarps;
-#pragma unroll
-            for (int e = 0; e < DPL; ++e) vf[j][e] = 0.f;
-            if (p < L) {
-                if (DPL == 4) {
-                    const uint2 u2 = *reinterpret_cast<const uint2*>(vc + static_cast<size_t>(p) * DH + lane * 4);
-                    vf[j][0] = bf_lo(u2.x); vf[j][1] = bf_hi(u2.x); vf[j][2 % DPL] = bf_lo(u2.y); vf[j][3 % DPL] = bf_hi(u2.y);
-                } else {
-                    const uint32_t u1 = *reinterpret_cast<const uint32_t*>(vc + static_cast<size_t>(p) * DH + lane * 2);
-                    vf[j][0] = bf_lo(u1); vf[j][1] = bf_hi(u1);
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-            const int p = pb + j * kAttnWarps;
-            if (p < L) {
-#pragma unroll
-                for (int gg = 0; gg < G; ++gg) {
-                    const float w = sc[gg * lcap + p];
-#pragma unroll
-                    for (int e = 0; e < DPL; ++e) acc[gg][e] += w * vf[j][e];
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int gg = 0; gg < G; ++gg)
-#pragma unroll
-        for (int e = 0; e < DPL; ++e) red[(warp * G + gg) * DH + lane * DPL + e] = acc[gg][e];
-    __syncthreads();
-    for (int e = threadIdx.x; e < G * DH; e += kAttnThreads) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < kAttnWarps; ++w) s += red[w * G * DH + e];
-        const int gg = e / DH, d = e - gg * DH;
-        a.out[(static_cast<size_t>(row) * a.H + g * G + gg) * DH + d] = f2bf(s);
-    }
+    attend<DH, G>(qs, sc, red, kc, vc, L, lcap, scale, a.bf16_math,
+                  a.out + (static_cast<size_t>(row) * a.H + g * G) * DH);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -515,112 +565,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(AttnDecodeArg
     const __nv_bfloat16* kc = a.kcache + cache_base;
     const __nv_bfloat16* vc = a.vcache + cache_base;
 
-    // ---- scores ----
-    constexpr int LPR = DH / 8;    // lanes per cache row (16-byte loads)
-    constexpr int RPW = 32 / LPR;  // rows per warp iteration
-    const int sub = lane / LPR, li = lane % LPR;
-    float qr[G][8];
-#pragma unroll
-    for (int gg = 0; gg < G; ++gg)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) qr[gg][e] = qs[gg * DH + li * 8 + e];
-    constexpr int UNR = 4;  // independent 16-byte loads in flight per lane
-    for (int pb = warp * RPW * UNR; pb < L; pb += kAttnWarps * RPW * UNR) {
-        uint4 u[UNR];
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-            const int p = pb + j * RPW + sub;
-            u[j] = make_uint4(0, 0, 0, 0);
-            if (p < L) u[j] = *reinterpret_cast<const uint4*>(kc + static_cast<size_t>(p) * DH + li * 8);
-        }
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-            const int p = pb + j * RPW + sub;
-            const bool ok = p < L;
-            const float kf[8] = {bf_lo(u[j].x), bf_hi(u[j].x), bf_lo(u[j].y), bf_hi(u[j].y),
-                                 bf_lo(u[j].z), bf_hi(u[j].z), bf_lo(u[j].w), bf_hi(u[j].w)};
-#pragma unroll
-            for (int gg = 0; gg < G; ++gg) {
-                float dd = 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) dd += qr[gg][e] * kf[e];
-#pragma unroll
-                for (int o = LPR / 2; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
-                if (ok && li == 0) sc[gg * lcap + p] = a.bf16_math ? rbf(rbf(dd) * scale) : dd * scale;
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- softmax (warp per head) ----
-    for (int gg = warp; gg < G; gg += kAttnWarps) {
-        float* s = sc + gg * lcap;
-        float m = -INFINITY;
-        for (int p = lane; p < L; p += 32) m = fmaxf(m, s[p]);
-        m = warp_max(m);
-        float z = 0.f;
-        for (int p = lane; p < L; p += 32) {
-            const float e = expf(s[p] - m);
-            s[p] = e;
-            z += e;
-        }
-        z = warp_sum(z);
-        for (int p = lane; p < L; p += 32) {
-            const float pr = s[p] / z;
-            s[p] = a.bf16_math ? rbf(pr) : pr;
-        }
-    }
-    __syncthreads();
-
-    // ---- P.V ----
-    constexpr int DPL = DH / 32;  // dims per lane
-    float acc[G][DPL];
-#pragma unroll
-    for (int gg = 0; gg < G; ++gg)
-#pragma unroll
-        for (int e = 0; e < DPL; ++e) acc[gg][e] = 0.f;
-    for (int pb = warp; pb < L; pb += kAttnWarps * UNR) {
-        float vf[UNR][DPL];
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-            const int p = pb + j * kAttnWarps;
-#pragma unroll
-            for (int e = 0; e < DPL; ++e) vf[j][e] = 0.f;
-            if (p < L) {
-                if (DPL == 4) {
-                    const uint2 u2 = *reinterpret_cast<const uint2*>(vc + static_cast<size_t>(p) * DH + lane * 4);
-                    vf[j][0] = bf_lo(u2.x); vf[j][1] = bf_hi(u2.x); vf[j][2 % DPL] = bf_lo(u2.y); vf[j][3 % DPL] = bf_hi(u2.y);
-                } else {
-                    const uint32_t u1 = *reinterpret_cast<const uint32_t*>(vc + static_cast<size_t>(p) * DH + lane * 2);
-                    vf[j][0] = bf_lo(u1); vf[j][1] = bf_hi(u1);
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) {
-            const int p = pb + j * kAttnWarps;
-            if (p < L) {
-#pragma unroll
-                for (int gg = 0; gg < G; ++gg) {
-                    const float w = sc[gg * lcap + p];
-#pragma unroll
-                    for (int e = 0; e < DPL; ++e) acc[gg][e] += w * vf[j][e];
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int gg = 0; gg < G; ++gg)
-#pragma unroll
-        for (int e = 0; e < DPL; ++e) red[(warp * G + gg) * DH + lane * DPL + e] = acc[gg][e];
-    __syncthreads();
-    for (int e = threadIdx.x; e < G * DH; e += kAttnThreads) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < kAttnWarps; ++w) s += red[w * G * DH + e];
-        const int gg = e / DH, dd = e - gg * DH;
-        a.out[(static_cast<size_t>(row) * a.H + g * G + gg) * DH + dd] = f2bf(s);
-    }
+    attend<DH, G>(qs, sc, red, kc, vc, L, lcap, scale, a.bf16_math,
+                  a.out + (static_cast<size_t>(row) * a.H + g * G) * DH);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -970,13 +916,30 @@ int launch_qkv_prep(const QkvPrepArgs& a, cudaStream_t st) {
     return 0;
 }
 
+// Score-buffer positions per head for a context bound of `need`: rounded up to a multiple of 32 and cut to what fits
+// 200 KB of shared memory (a longer context is walked in chunks, see attend()).  g_attn_chunk (tests) forces a chunk.
+static int g_attn_chunk = 0;
+void attn_set_score_chunk(int positions) { g_attn_chunk = positions > 0 ? (positions + 31) / 32 * 32 : 0; }
+template <int DH, int G>
+static size_t attn_smem_bytes(int lcap) {
+    return (static_cast<size_t>(G) * DH + static_cast<size_t>(G) * lcap + static_cast<size_t>(kAttnWarps) * G * DH) *
+           sizeof(float);
+}
+template <int DH, int G>
+static int attn_score_chunk(int need) {
+    int lcap = (need + 31) / 32 * 32;
+    const int fit = static_cast<int>((200 * 1024 - attn_smem_bytes<DH, G>(0)) / (sizeof(float) * G)) / 32 * 32;
+    if (lcap > fit) lcap = fit;
+    if (g_attn_chunk > 0 && g_attn_chunk < lcap) lcap = g_attn_chunk;
+    return lcap;
+}
+
 template <int DH, int G>
 static int launch_attn_t(const AttnArgs& a, cudaStream_t st) {
     int lcap = a.window > 0 && a.window < a.S ? a.window : a.S;
     if (a.lcap > 0 && a.lcap < lcap) lcap = a.lcap;
-    const size_t smem = (static_cast<size_t>(G) * DH + static_cast<size_t>(G) * lcap +
-                         static_cast<size_t>(kAttnWarps) * G * DH) * sizeof(float);
-    FSB_CHECK(smem <= 200 * 1024, "attention: context %d too long for the shared-memory score buffer", lcap);
+    lcap = attn_score_chunk<DH, G>(lcap);
+    const size_t smem = attn_smem_bytes<DH, G>(lcap);
     const float scale = 1.0f / sqrtf(static_cast<float>(DH));
     FSB_LAUNCH((attn_kernel<DH, G>), dim3(a.Hkv, a.rows), dim3(kAttnThreads), smem, st, a, scale, lcap);
     return 0;
@@ -999,9 +962,8 @@ template <int DH, int G>
 static int launch_attn_decode_t(const AttnDecodeArgs& a, cudaStream_t st) {
     int lcap = a.S;
     if (a.lcap > 0 && a.lcap < lcap) lcap = a.lcap;
-    const size_t smem = (static_cast<size_t>(G) * DH + static_cast<size_t>(G) * lcap +
-                         static_cast<size_t>(kAttnWarps) * G * DH) * sizeof(float);
-    FSB_CHECK(smem <= 200 * 1024, "attention: context %d too long for the shared-memory score buffer", lcap);
+    lcap = attn_score_chunk<DH, G>(lcap);
+    const size_t smem = attn_smem_bytes<DH, G>(lcap);
     const float scale = 1.0f / sqrtf(static_cast<float>(DH));
     FSB_LAUNCH((attn_decode_kernel<DH, G>), dim3(a.Hkv, a.rows), dim3(kAttnThreads), smem, st, a, scale, lcap);
     return 0;

@@ -95,6 +95,7 @@ struct AttnArgs {
 };
 int launch_attn(const AttnArgs& a, cudaStream_t st);
 int attn_init();  // set kernel attributes (idempotent)
+void attn_set_score_chunk(int positions);  // tests: force the score-buffer chunk (0 = automatic)
 
 // Decode-step attention: the consumer of the qkv step GEMM. One CTA per (batch row, KV group) first finishes that
 // GEMM for its own (G + 2) heads -- slot-ordered sum of the stream-K partials, bias, per-head nn.RMSNorm, interleaved

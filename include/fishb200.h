@@ -164,10 +164,15 @@ int fsb_lm_buffer(fsb_lm* h, const char* name, void** d_ptr, size_t* bytes);
 int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* launches_per_rep,
                        void* stream);
 
-/* Diagnostic: the step GEMMs of the first slow layers (qkv, wo, w1|w3, w2, ...) launched back to back with per-CTA
- * globaltimer stamps: d_trace[launch][512][8] = {start, operand fetch allowed, first accumulator complete, partials
- * published, all partials of the last shared tile present, end, smid, items}. Returns the number of launches traced
- * (0 = failure); overwrites the decode state like fsb_lm_bench_gemms. */
+/* Diagnostics: per-CTA globaltimer stamps of step GEMM launches, d_trace[launch][512][8] = {start, previous grid
+ * complete (griddepcontrol.wait returned), -, -, first accumulator complete, end, normaliser warps ready,
+ * first operand tile normalised} (0 = not recorded).
+ * fsb_lm_trace_step_gemms: the step GEMMs of the first slow layers (qkv, wo, w1|w3, w2, ...) launched back to back;
+ * returns the number of launches traced (0 = failure); overwrites the decode state like fsb_lm_bench_gemms.
+ * fsb_lm_trace_frame: ONE whole decode frame (eager launches, the kernels and launch attributes of the graph), every
+ * step GEMM traced in launch order; advances the decode state by one frame; returns the launches traced or -1. */
+int fsb_lm_trace_frame(fsb_lm* h, int batch, const fsb_sampling* sampling, unsigned long long* d_trace,
+                       int max_launches, void* stream);
 int fsb_lm_trace_step_gemms(fsb_lm* h, unsigned long long* d_trace, int max_launches, int* grid_out, void* stream);
 
 /* Test hook for bit-exact parity of the STOCHASTIC sampler with the reference's torch RNG stream
@@ -234,6 +239,10 @@ int fsb_swiglu_f32(const float* d_y, int rows, int I, void* d_h, void* stream);
  * bn in {32,64,128,256}; streamk_ctas > 0 uses the decode-style stream-K schedule + partial sums. */
 int fsb_op_gemm(const void* d_a, const void* d_b, float* d_out, int m, int n, int k, int bn,
                 int streamk_ctas, void* stream);
+
+/* Attention keeps one fp32 score per position and head in shared memory; contexts longer than the buffer are walked
+ * in chunks, bit-identically (csrc/lm_kernels.cu attend()).  positions > 0 forces a smaller chunk; 0 = automatic. */
+int fsb_op_attn_score_chunk(int positions);
 
 #ifdef __cplusplus
 }

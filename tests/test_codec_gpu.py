@@ -116,7 +116,8 @@ def test_indices_clamped_in_place_like_reference(tiny):
 # except where the GPU's choice is a near-tie under the ORACLE's own fp32 scores: at the first residual stage
 # where a frame's code differs, score_oracle(best) - score_oracle(GPU's code) <= VQ_EPS (scores are
 # 2*cos - 2 in [-4, 0]); later stages of that frame quantise a different residual and are not comparable.
-VQ_EPS = 0.05
+# Calibration (B200, this file's five cases incl. the full 391 M geometry): worst observed gap 0.0133.
+VQ_EPS = 0.03
 
 
 def vq_first_mismatches(scores, ref_codes, got_codes):
@@ -242,7 +243,7 @@ def test_streaming_decode_equals_one_shot(tiny, full):
     print(f"streamed vs one-shot decode ({'full' if full else 'tiny'}): SNR {s:.1f} dB, bitwise equal: {torch.equal(got, ref)}")
     assert s >= 80.0, f"streamed decode differs from the one-shot decode: SNR {s:.1f} dB"
     with pytest.raises(ValueError):
-        st.push(codes[:, :, :200].clone())  # over the stream's capacity
+        st.push(codes.repeat(1, 1, 8)[:, :, :256 - T + 1].clone())  # one frame over the stream's capacity
 
 
 def test_bulk_encode_with_the_real_codec(tiny, tmp_path):

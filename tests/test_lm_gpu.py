@@ -312,7 +312,9 @@ def test_full_s2pro_geometry_batch32():
     """The real size: 36 + 4 layers at S2-Pro dimensions (dim 2560, 32/8 heads x 128, I 9728, 10 x 4096 codes, the 4097
     selectable head rows), batch 32 -- the benchmark's configuration. Sequences 0, 13 and 31 of the batch are checked
     against the CPU oracle run on each of them alone: token ids and codes identical up to the first decision the oracle
-    itself took on a bf16 near-tie (random weights, 4096-way decisions). Vocabulary reduced to keep the CPU side short."""
+    itself took on a bf16 near-tie (random weights, 4096-way decisions). Vocabulary reduced to keep the CPU side short.
+    Near-tie = oracle top-2 gap <= 3 x 2^-7 of the top logit here (2 x on the tiny models): through 36 layers the two
+    implementations' fp32 summation orders differ by more bf16 roundings of the residual stream."""
     from fish_speech_b200.models.text2semantic.inference import generate_batch
 
     cfg = O.LMConfig(vocab_size=8192, max_seq_len=128, semantic_begin_id=4000, semantic_end_id=8095, im_end_id=3999)
@@ -328,7 +330,8 @@ def test_full_s2pro_geometry_batch32():
         ref = O.generate(O.setup(cfg, w) if i else st, prompts[i], 3, temperature=0.7, top_p=0.7, top_k=1, traces=traces,
                          stop_on_im_end=False, noise=False)
         T = prompts[i].shape[1]
-        frames = assert_tokens_match(outs[i][:, : ref.shape[1]], ref, traces, cfg, T, f"full size, sequence {i}")
+        frames = assert_tokens_match(outs[i][:, : ref.shape[1]], ref, traces, cfg, T, f"full size, sequence {i}",
+                                     tie_ulps=3.0)
         got, want = outs[i].cpu().to(torch.int32), ref.to(torch.int32)
         f = T + frames
         verified += frames * cfg.num_codebooks
