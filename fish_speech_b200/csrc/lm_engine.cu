@@ -103,6 +103,8 @@ struct fsb_lm {
     int ctx_lcap = 0;  // score-buffer bound for the slow attention (0 = capacity)
     unsigned long long* trace_base = nullptr;  // fsb_lm_trace_frame: per-CTA stamps of every step GEMM of one frame
     int trace_next = 0, trace_max = 0;
+    unsigned long long* attn_trace_base = nullptr;  // 8 stamps of CTA (0, 0) of every decode attention launch
+    int attn_trace_next = 0, attn_trace_max = 0;
     int graph_lcap = -1;
     // decode graph cache
     cudaGraphExec_t graph_exec = nullptr;
@@ -231,6 +233,8 @@ int run_stack_decode(fsb_lm* h, Stack& s, int rows, const int* row_seq, const in
         aa.bf16_math = s.bf16_math;
         aa.kv_only = (stop_after_kv && l == s.nl - 1) ? 1 : 0;  // fast pass 0 only fills the KV cache (inference.py:147)
         aa.eps = eps;
+        if (h->attn_trace_base && h->attn_trace_next < h->attn_trace_max)
+            aa.trace = h->attn_trace_base + static_cast<size_t>(h->attn_trace_next++) * 8;
         FSB_TRY(launch_attn_decode(aa, st));
         if (aa.kv_only) return 0;
         FSB_TRY(launch(P.wo));
@@ -824,7 +828,7 @@ int fsb_lm_copy_kv(fsb_lm* h, int src_slot, int dst_slot, int n_pos, void* strea
 }
 
 int fsb_lm_trace_frame(fsb_lm* h, int batch, const fsb_sampling* sp, unsigned long long* d_trace, int max_launches,
-                       void* stream) {
+                       unsigned long long* d_attn_trace, int max_attn, void* stream) {
     // Diagnostic: ONE decode frame, eager launches (same kernels, same programmatic dependent launch as the graph),
     // every step GEMM recording its per-CTA stamps in launch order: the in-frame timeline at GEMM granularity.
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -833,11 +837,28 @@ int fsb_lm_trace_frame(fsb_lm* h, int batch, const fsb_sampling* sp, unsigned lo
     h->trace_base = d_trace;
     h->trace_next = 0;
     h->trace_max = max_launches;
+    h->attn_trace_base = d_attn_trace;
+    h->attn_trace_next = 0;
+    h->attn_trace_max = d_attn_trace ? max_attn : 0;
     const int rc = decode_one_frame(h, batch, *sp, st);
     const int n = h->trace_next;
+    h->attn_trace_base = nullptr;
     h->trace_base = nullptr;
     h->trace_next = h->trace_max = 0;
     return rc != 0 ? -1 : n;
+}
+
+int fsb_lm_repeat_step_gemm(fsb_lm* h, int layer, int kind, int reps, void* stream) {
+    // Diagnostic: the SAME step GEMM of one slow layer `reps` times back to back: from the second launch on its weights
+    // come from L2 where they fit (126 MB), which separates "bound by HBM" from "bound by the SM-side pipeline".
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Stack& s = h->slow;
+    FSB_CHECK(layer >= 0 && layer < s.nl && kind >= 0 && kind < 4, "repeat_step_gemm: layer %d kind %d", layer, kind);
+    const StepGemmPlan* plans[4] = {&s.dec[layer].qkv, &s.dec[layer].wo, &s.dec[layer].w13, &s.dec[layer].w2};
+    StepGemmPlan q = *plans[kind];
+    q.p.rows = h->cfg.max_batch;
+    for (int i = 0; i < reps; ++i) FSB_TRY(step_gemm_launch(q, st));
+    return 0;
 }
 
 int fsb_lm_trace_step_gemms(fsb_lm* h, unsigned long long* d_trace, int max_launches, int* grid_out, void* stream) {

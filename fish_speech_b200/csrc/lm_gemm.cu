@@ -52,17 +52,18 @@ __device__ __forceinline__ void rows_warp_sums(const float (&sq)[R], float* red,
 template <int R, int UQ>  // UQ = partials fetched per round
 __device__ __forceinline__ void prev_sums(const StepGemmParams& p, int tile, int tid, int j0, float (&acc)[R]) {
     const int np = __ldg(p.prev.nparts + tile);
+    const int maxp = p.prev.max_parts;  // loads are bounded by the launch constant, see step_partial_sum
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.f;
     const float* src = p.prev.ws + (static_cast<size_t>(tile) * 32 + j0) * 128 + tid;
     const size_t sstride = static_cast<size_t>(p.prev.tiles) * 32 * 128;
-    for (int q0 = 0; q0 < np; q0 += UQ) {
+    for (int q0 = 0; q0 < maxp; q0 += UQ) {
         float t[UQ][R];
 #pragma unroll
         for (int u = 0; u < UQ; ++u)
 #pragma unroll
             for (int r = 0; r < R; ++r)
-                t[u][r] = (q0 + u < np && j0 + r < p.rows) ? __ldcg(src + static_cast<size_t>(q0 + u) * sstride + r * 128) : 0.f;
+                t[u][r] = (q0 + u < maxp && j0 + r < p.rows) ? __ldcg(src + static_cast<size_t>(q0 + u) * sstride + r * 128) : 0.f;
 #pragma unroll
         for (int u = 0; u < UQ; ++u) {
             if (q0 + u < np) {
@@ -110,7 +111,7 @@ __device__ __forceinline__ void pro_swiglu(const StepGemmParams& p, int tile, in
     const bool hi = (lane & 16) != 0;  // lanes 16..31 hold the w3 ("up") rows of the features lanes 0..15 gate
     const int f = tile * 64 + quad * 16 + (lane & 15);
     float acc[R];
-    prev_sums<R, (R == 32 ? 2 : 32 / R)>(p, tile, tid, j0, acc);  // (this kernel has 192 threads: registers to spare)
+    prev_sums<R, (R == 32 ? 2 : (R == 16 ? 3 : 32 / R))>(p, tile, tid, j0, acc);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const float up = __shfl_xor_sync(0xffffffffu, acc[r], 16);
@@ -524,6 +525,7 @@ StepPartials step_plan_partials(const StepGemmPlan& plan) {
     P.nparts = plan.nparts_dev;
     P.tiles = plan.p.tiles;
     P.n_out = plan.p.n_out;
+    P.max_parts = plan.max_parts;
     return P;
 }
 
@@ -546,7 +548,11 @@ int step_finalize_launch(const StepGemmPlan& consumer, cudaStream_t st) {
     const int pro = consumer.pro;
     if (pro == PRO_NONE) return 0;
     StepGemmParams p = consumer.p;
-    const int rb = pro == PRO_SWIGLU ? 8 : 2;  // one load round per unit (<= 4 / <= 16 partials), every unit on its own CTA
+    // one load round per unit (<= 4 / <= 16 partials), every unit on its own CTA
+    static const int rb_swiglu = [] { const char* e = getenv("FSB_SWIGLU_RB"); return e ? atoi(e) : 8; }();
+    static const int rb_resid = [] { const char* e = getenv("FSB_RESID_RB"); return e ? atoi(e) : 2; }();
+    const int rb = pro == PRO_SWIGLU ? rb_swiglu : rb_resid;
+    FSB_CHECK(rb >= 1 && rb <= 32 && (rb & (rb - 1)) == 0, "finalize: row block %d is not a power of two <= 32", rb);
     p.prev_rb = rb;
     const int units = p.prev.tiles * cdiv(p.rows, rb);
     if (pro == PRO_RESID) FSB_LAUNCH(step_finalize_kernel<PRO_RESID>, dim3(units), dim3(kEpiThreads), 0, st, p);

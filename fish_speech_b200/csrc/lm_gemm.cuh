@@ -42,7 +42,8 @@ struct StepPartials {
     const float* ws;
     const int* nparts;  // [tiles]
     int tiles;
-    int n_out;  // output features (rows of the weight matrix)
+    int n_out;      // output features (rows of the weight matrix)
+    int max_parts;  // max over tiles of nparts: slots [0, max_parts) exist in ws for every tile
 };
 
 #ifdef __CUDACC__
@@ -53,10 +54,12 @@ __device__ __forceinline__ float step_partial_sum(const StepPartials& P, int row
     const float* p = P.ws + (static_cast<size_t>(tile) * 32 + row) * 128 + (feat & 127);
     const size_t ss = static_cast<size_t>(P.tiles) * 32 * 128;
     float s = 0.f;
-    for (int q = 0; q < np; q += 8) {  // eight loads in flight, additions in slot order
+    // The loads are bounded by max_parts (a launch constant), not by this tile's count: they leave together with
+    // the load of the count instead of one round trip behind it; slots >= np hold stale data and are not added.
+    for (int q = 0; q < P.max_parts; q += 8) {  // eight loads in flight, additions in slot order
         float a[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) a[u] = q + u < np ? __ldcg(p + static_cast<size_t>(q + u) * ss) : 0.f;
+        for (int u = 0; u < 8; ++u) a[u] = q + u < P.max_parts ? __ldcg(p + static_cast<size_t>(q + u) * ss) : 0.f;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
             if (q + u < np) s += a[u];
@@ -71,21 +74,20 @@ __device__ __forceinline__ void step_partial_sums(const StepPartials& P, int row
     const size_t ss = static_cast<size_t>(P.tiles) * 32 * 128;
     int np[N];
     const float* p[N];
-    int maxp = 0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         const int f = ok[k] ? feat[k] : 0;
         np[k] = ok[k] ? __ldg(P.nparts + (f >> 7)) : 0;
         p[k] = P.ws + (static_cast<size_t>(f >> 7) * 32 + row) * 128 + (f & 127);
         out[k] = 0.f;
-        maxp = max(maxp, np[k]);
     }
-    for (int q = 0; q < maxp; q += 8) {
+    for (int q = 0; q < P.max_parts; q += 8) {  // bounded by the launch constant: see step_partial_sum
         float a[N][8];
 #pragma unroll
         for (int k = 0; k < N; ++k)
 #pragma unroll
-            for (int u = 0; u < 8; ++u) a[k][u] = q + u < np[k] ? __ldcg(p[k] + static_cast<size_t>(q + u) * ss) : 0.f;
+            for (int u = 0; u < 8; ++u)
+                a[k][u] = (ok[k] && q + u < P.max_parts) ? __ldcg(p[k] + static_cast<size_t>(q + u) * ss) : 0.f;
 #pragma unroll
         for (int k = 0; k < N; ++k)
 #pragma unroll

@@ -280,6 +280,7 @@ __global__ void qkv_prep_kernel(QkvPrepArgs a) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kAttnThreads = 256;
 constexpr int kAttnWarps = kAttnThreads / 32;
+constexpr int kAttnPrefetchPos = 2048;  // positions of K/V history the decode attention prefetches to L2 (8 lines per thread)
 
 // Softmax(q k^T) v of one query token against positions [0, L) of one KV group: all G query heads of the group at once.
 // The score buffer holds `lcap` positions per head (a multiple of 32).  A context that fits is scored once; a longer
@@ -289,7 +290,7 @@ constexpr int kAttnWarps = kAttnThreads / 32;
 template <int DH, int G>
 __device__ __forceinline__ void attend(const float* qs, float* sc, float* red, const __nv_bfloat16* kc,
                                        const __nv_bfloat16* vc, int L, int lcap, float scale, int bf16_math,
-                                       __nv_bfloat16* out) {
+                                       __nv_bfloat16* out, unsigned long long* trace = nullptr) {
     static_assert(G <= kAttnWarps, "one warp per query head in the softmax");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int LPR = DH / 8;    // lanes per cache row (16-byte loads)
@@ -337,6 +338,7 @@ __device__ __forceinline__ void attend(const float* qs, float* sc, float* red, c
     float m = -INFINITY, z = 0.f;  // of head `warp` (warps < G)
     if (one) {
         scores(0, L);
+        if (trace && threadIdx.x == 0) trace[4] = globaltimer_ns();
         if (warp < G) {
             float* s = sc + warp * lcap;
             for (int p = lane; p < L; p += 32) m = fmaxf(m, s[p]);
@@ -353,6 +355,7 @@ __device__ __forceinline__ void attend(const float* qs, float* sc, float* red, c
             }
         }
         __syncthreads();
+        if (trace && threadIdx.x == 0) trace[5] = globaltimer_ns();
     } else {
         for (int c0 = 0; c0 < L; c0 += lcap) {
             const int n = min(lcap, L - c0);
@@ -428,12 +431,14 @@ __device__ __forceinline__ void attend(const float* qs, float* sc, float* red, c
 #pragma unroll
         for (int e = 0; e < DPL; ++e) red[(warp * G + gg) * DH + lane * DPL + e] = acc[gg][e];
     __syncthreads();
+    if (trace && threadIdx.x == 0) trace[6] = globaltimer_ns();
     for (int e = threadIdx.x; e < G * DH; e += kAttnThreads) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kAttnWarps; ++w) s += red[w * G * DH + e];
         out[e] = f2bf(s);
     }
+    if (trace && threadIdx.x == 0) trace[7] = globaltimer_ns();
 }
 
 
@@ -474,29 +479,53 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kernel(AttnArgs a, float sc
 // ------------------------------------------------------------------------------------------------
 template <int DH, int G>
 __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(AttnDecodeArgs a, float scale, int lcap) {
+    unsigned long long* trace = (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) ? a.trace : nullptr;
+    if (trace && threadIdx.x == 0) trace[0] = globaltimer_ns();
     pdl_launch_dependents();
+    const int row = blockIdx.y, g = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- before the qkv GEMM has finished: pull this row's K/V history towards L2.  The cache lines of positions
+    // < pos were written frames ago; the position read here may be one frame stale (it only steers prefetch hints,
+    // the real one is read after the dependency wait).  The scores / values loops then find L2 hits instead of paying
+    // the HBM latency while the next GEMM's weight prefetch keeps the memory queues full. ----
+    {
+        const int pb = a.row_seq[row];
+        const int pp = min(max(a.row_pos[row], 0), a.S - 1);
+        const int n = min(pp + 1, kAttnPrefetchPos);
+        const size_t base = (static_cast<size_t>(pb) * a.Hkv + g) * a.S * DH;
+        const int lines = n * DH * 2 / 128;  // 128-byte lines of K (and as many of V)
+        for (int i = threadIdx.x; i < lines; i += kAttnThreads) {
+            prefetch_l2(reinterpret_cast<const char*>(a.kcache + base) + static_cast<size_t>(i) * 128);
+            prefetch_l2(reinterpret_cast<const char*>(a.vcache + base) + static_cast<size_t>(i) * 128);
+        }
+    }
+    // what the front end needs besides the GEMM result (static data): requested before the wait as well
+    constexpr int HPR = kAttnThreads / DH;   // heads per round
+    constexpr int WPH = DH / 32;             // warps per head
+    constexpr int NH = G + 2;
+    constexpr int NR = (NH + HPR - 1) / HPR;  // rounds: this thread's features, one per round
+    const int hsub = threadIdx.x / DH, d = threadIdx.x % DH;
+    float bias_r[NR], normw_r[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int hh = r * HPR + hsub;
+        const int kind = hh < G ? 0 : (hh == G ? 1 : 2);
+        const int head = kind == 0 ? g * G + hh : (kind == 1 ? a.H + g : a.H + a.Hkv + g);
+        const __nv_bfloat16* nw = kind == 0 ? a.q_norm : (kind == 1 ? a.k_norm : nullptr);
+        bias_r[r] = (a.bias != nullptr && hh < NH) ? bf2f(a.bias[head * DH + d]) : 0.f;
+        normw_r[r] = (nw != nullptr && hh < NH) ? bf2f(nw[d]) : 0.f;
+    }
     pdl_wait();
+    if (trace && threadIdx.x == 0) trace[1] = globaltimer_ns();
     extern __shared__ float sm[];
     float* qs = sm;                      // [G][DH]
     float* sc = qs + G * DH;             // [G][lcap]
     float* red = sc + G * lcap;          // [kAttnWarps][G][DH]
-    __shared__ float wred[kAttnWarps];
-    const int row = blockIdx.y, g = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ float wred[NR][kAttnWarps];
+    // ---- finish the qkv GEMM for this row's heads: q heads g*G .. g*G+G-1, then k, then v of KV group g.  The
+    // partials are requested before the row's position is looked at (they do not depend on it) ----
     const int b = a.row_seq[row];
     const int rpos = a.row_pos[row];
-    if (rpos < 0) {  // idle slot parked at position -1: neither the cache nor the output row is touched
-        return;
-    }
-    // ---- finish the qkv GEMM for this row's heads: q heads g*G .. g*G+G-1, then k, then v of KV group g ----
-    constexpr int HPR = kAttnThreads / DH;   // heads per round
-    constexpr int WPH = DH / 32;             // warps per head
-    constexpr int NH = G + 2;
-    const int hsub = threadIdx.x / DH, d = threadIdx.x % DH;
-    const int wpos = min(rpos, a.S - 1);
-    constexpr int NR = (NH + HPR - 1) / HPR;  // rounds: this thread's features, one per round
-    // (cos, sin) of this lane's rotary pair at the row's position: the same for q and k, requested before the partials
-    const uint32_t cs = *reinterpret_cast<const uint32_t*>(a.freqs + (static_cast<size_t>(wpos) * (DH / 2) + (d >> 1)) * 2);
     float vsum[NR];
     {
         int feat[NR];
@@ -511,53 +540,65 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(AttnDecodeArg
         }
         step_partial_sums<NR>(a.qkv, row, feat, ok, vsum);  // every partial of every round in flight at once
     }
+    if (rpos < 0) {  // idle slot parked at position -1: neither the cache nor the output row is touched
+        return;
+    }
+    const int wpos = min(rpos, a.S - 1);
+    // (cos, sin) of this lane's rotary pair at the row's position: the same for q and k
+    const uint32_t cs = *reinterpret_cast<const uint32_t*>(a.freqs + (static_cast<size_t>(wpos) * (DH / 2) + (d >> 1)) * 2);
+    if (trace && threadIdx.x == 0) trace[2] = globaltimer_ns() + (vsum[0] == 12345.f ? 1 : 0);  // after the sums arrive
+    // bias, the GEMM output's bf16 rounding, and per-head nn.RMSNorm (fp32 math, weight multiply included, ONE
+    // rounding): the sums of squares of all rounds cross the warps behind one barrier
+    const bool any_norm = a.q_norm != nullptr || a.k_norm != nullptr;
+    float v[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        const int r0 = r * HPR;
-        const int hh = r0 + hsub;
+        const int hh = r * HPR + hsub;
+        v[r] = 0.f;
+        if (hh < NH) {
+            v[r] = vsum[r];
+            if (a.bias) v[r] += bias_r[r];
+            v[r] = rbf(v[r]);
+        }
+        if (any_norm) {
+            const float ws = warp_sum(v[r] * v[r]);
+            if (lane == 0) wred[r][warp] = ws;
+        }
+    }
+    if (any_norm) __syncthreads();
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int hh = r * HPR + hsub;
         const bool live = hh < NH;
         const int kind = hh < G ? 0 : (hh == G ? 1 : 2);
-        const int head = kind == 0 ? g * G + hh : (kind == 1 ? a.H + g : a.H + a.Hkv + g);
-        const int f = head * DH + d;
-        float v = 0.f;
-        if (live) {
-            v = vsum[r];
-            if (a.bias) v += bf2f(a.bias[f]);
-            v = rbf(v);
-        }
-        const __nv_bfloat16* nw = kind == 0 ? a.q_norm : (kind == 1 ? a.k_norm : nullptr);
-        if (a.q_norm != nullptr || a.k_norm != nullptr) {
-            // nn.RMSNorm(head_dim): fp32 math, weight multiply included, ONE rounding
-            const float ws = warp_sum((live && nw != nullptr) ? v * v : 0.f);
-            __syncthreads();
-            if (lane == 0) wred[warp] = ws;
-            __syncthreads();
-            if (live && nw != nullptr) {
-                const int w0 = (warp / WPH) * WPH;
-                float tot = 0.f;
+        const bool normed = kind == 0 ? a.q_norm != nullptr : (kind == 1 ? a.k_norm != nullptr : false);
+        float x = v[r];
+        if (live && normed) {
+            const int w0 = (warp / WPH) * WPH;
+            float tot = 0.f;
 #pragma unroll
-                for (int u = 0; u < WPH; ++u) tot += wred[w0 + u];
-                const float rinv = rsqrtf(tot / static_cast<float>(DH) + a.eps);
-                v = rbf(v * rinv * bf2f(nw[d]));
-            }
+            for (int u = 0; u < WPH; ++u) tot += wred[r][w0 + u];
+            const float rinv = rsqrtf(tot / static_cast<float>(DH) + a.eps);
+            x = rbf(x * rinv * normw_r[r]);
         }
         if (kind != 2) {
-            const float c = bf_lo(cs), s = bf_hi(cs);
-            const float partner = __shfl_xor_sync(0xffffffffu, v, 1);
-            v = (lane & 1) ? __fadd_rn(__fmul_rn(v, c), __fmul_rn(partner, s)) : __fsub_rn(__fmul_rn(v, c), __fmul_rn(partner, s));
-            v = rbf(v);
+            const float c = bf_lo(cs), sn = bf_hi(cs);
+            const float partner = __shfl_xor_sync(0xffffffffu, x, 1);
+            x = (lane & 1) ? __fadd_rn(__fmul_rn(x, c), __fmul_rn(partner, sn)) : __fsub_rn(__fmul_rn(x, c), __fmul_rn(partner, sn));
+            x = rbf(x);
         }
         if (live) {
             if (kind == 0) {
-                qs[hh * DH + d] = v;
+                qs[hh * DH + d] = x;
             } else if (rpos < a.S) {
                 __nv_bfloat16* cache = kind == 1 ? a.kcache : a.vcache;
-                cache[((static_cast<size_t>(b) * a.Hkv + g) * a.S + rpos) * DH + d] = f2bf(v);
+                cache[((static_cast<size_t>(b) * a.Hkv + g) * a.S + rpos) * DH + d] = f2bf(x);
             }
         }
     }
     if (a.kv_only) return;
     __syncthreads();  // q in shared memory, this row's new K/V visible to the whole CTA
+    if (trace && threadIdx.x == 0) trace[3] = globaltimer_ns();
 
     const int pos = wpos;
     const int L = pos + 1;
@@ -566,7 +607,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(AttnDecodeArg
     const __nv_bfloat16* vc = a.vcache + cache_base;
 
     attend<DH, G>(qs, sc, red, kc, vc, L, lcap, scale, a.bf16_math,
-                  a.out + (static_cast<size_t>(row) * a.H + g * G) * DH);
+                  a.out + (static_cast<size_t>(row) * a.H + g * G) * DH, trace);
 }
 
 // ------------------------------------------------------------------------------------------------

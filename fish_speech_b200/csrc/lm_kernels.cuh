@@ -118,6 +118,9 @@ struct AttnDecodeArgs {
     int bf16_math;  // the fast stack's all-bf16 attention (llama.py:948-976)
     int kv_only;
     float eps;
+    // diagnostics: optional 8 globaltimer stamps of CTA (0, 0): {start, wait returned, partials summed, q/k/v finished,
+    // scores done, softmax done, values summed, end}
+    unsigned long long* trace;
 };
 int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st);
 

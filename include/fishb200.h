@@ -169,10 +169,15 @@ int fsb_lm_bench_gemms(fsb_lm* h, int reps, double* weight_bytes_per_rep, int* l
  * first operand tile normalised} (0 = not recorded).
  * fsb_lm_trace_step_gemms: the step GEMMs of the first slow layers (qkv, wo, w1|w3, w2, ...) launched back to back;
  * returns the number of launches traced (0 = failure); overwrites the decode state like fsb_lm_bench_gemms.
+ * fsb_lm_repeat_step_gemm: the SAME step GEMM of one slow layer `reps` times back to back (weights from L2 after the
+ * first launch, where they fit); overwrites the decode state.
  * fsb_lm_trace_frame: ONE whole decode frame (eager launches, the kernels and launch attributes of the graph), every
- * step GEMM traced in launch order; advances the decode state by one frame; returns the launches traced or -1. */
+ * step GEMM traced in launch order; advances the decode state by one frame; returns the launches traced or -1.
+ * d_attn_trace (optional) [max_attn][8]: stamps of CTA (0, 0) of every decode attention launch = {start, wait returned,
+ * qkv partials summed, q/k/v finished, scores, softmax, values summed, end}. */
+int fsb_lm_repeat_step_gemm(fsb_lm* h, int layer, int kind, int reps, void* stream); /* kind: 0 qkv, 1 wo, 2 w1|w3, 3 w2 */
 int fsb_lm_trace_frame(fsb_lm* h, int batch, const fsb_sampling* sampling, unsigned long long* d_trace,
-                       int max_launches, void* stream);
+                       int max_launches, unsigned long long* d_attn_trace, int max_attn, void* stream);
 int fsb_lm_trace_step_gemms(fsb_lm* h, unsigned long long* d_trace, int max_launches, int* grid_out, void* stream);
 
 /* Test hook for bit-exact parity of the STOCHASTIC sampler with the reference's torch RNG stream

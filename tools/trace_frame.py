@@ -67,7 +67,8 @@ def main():
         trace = torch.zeros(n + 8, 512, 8, dtype=torch.int64, device=dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        got = L.fsb_lm_trace_frame(eng.h, B, C.byref(sp), trace.data_ptr(), n + 8, st)
+        atr = torch.zeros(512, 8, dtype=torch.int64, device=dev)
+        got = L.fsb_lm_trace_frame(eng.h, B, C.byref(sp), trace.data_ptr(), n + 8, atr.data_ptr(), 512, st)
         ev1.record()
         torch.cuda.synchronize()
         assert got == n, (got, n, L.fsb_last_error())
@@ -88,7 +89,7 @@ def main():
         early = (wait - s0) / 1e3
         k = agg.setdefault(names[i], [0, 0.0, 0.0, 0.0])
         k[0] += 1; k[1] += gap; k[2] += dep; k[3] += early
-        rows.append((i, names[i], gap, dep, early, len(r)))
+        rows.append((i, names[i], gap, dep, early, len(r), wait, end))
         prev_end = end
         first_start = s0 if first_start is None else first_start
         last_end = end
@@ -101,8 +102,25 @@ def main():
         print(f"| {name} | {c} | {g / c:.2f} | {d / c:.2f} | {e / c:.2f} | {g:.0f} | {d:.0f} |")
         tg += g; td += d
     print(f"| all | {n} | | | | {tg:.0f} | {td:.0f} |")
+    at = atr.cpu().double()
+    at = at[at[:, 0] > 0]
+    ns, nf = cfg.n_layer, at.shape[0] - cfg.n_layer
+    labels = ["start->wait", "wait->partials summed", "->q/k/v finished", "->scores", "->softmax", "->values", "->end"]
+    for name, blk in (("slow attention", at[:ns]), ("fast attention", at[ns:])):
+        blk = blk[blk[:, 7] > 0]  # KV-only launches stop after the cache write
+        if len(blk) == 0:
+            continue
+        d = (blk[:, 1:] - blk[:, :-1]) / 1e3
+        print(f"{name}, CTA (0,0), {len(blk)} launches, mean us: " +
+              ", ".join(f"{lab} {float(d[:, i].mean()):.2f}" for i, lab in enumerate(labels)) +
+              f"; wait->end {float((blk[:, 7] - blk[:, 1]).mean()) / 1e3:.2f}")
+    # boundaries around the slow attention: qkv GEMM's last CTA end -> attention's wait returned; attention end -> wo's wait
+    b1 = [float(at[l, 1]) - rows[4 * l][7] for l in range(ns)]
+    b2 = [rows[4 * l + 1][6] - float(at[l, 7]) for l in range(ns)]
+    print(f"slow attention boundaries, mean us: qkv GEMM end -> attention may run {sum(b1) / ns / 1e3:.2f}; "
+          f"attention CTA (0,0) end -> wo GEMM may run {sum(b2) / ns / 1e3:.2f}")
     if a.every:
-        for i, nm, g, d, e, ctas in rows[:: a.every]:
+        for i, nm, g, d, e, ctas, _w, _e in rows[:: a.every]:
             print(f"{i:4d} {nm:10s} gap {g:6.2f} dep {d:6.2f} early {e:6.2f} ctas {ctas}")
 
 
