@@ -327,6 +327,20 @@ int fsb_conv_gemm(const void* d_x, int B, int T_in, int C_in, int row_stride, lo
     return gemm_launch(plan, st);
 }
 
+// One decoder ResidualUnit (Snake -> dilated conv7 -> Snake -> conv1 -> + x) as one kernel: csrc/codec_resunit.cu.
+int fsb_res_unit_supported(int C) { return res_unit_supported(C) ? 1 : 0; }
+int fsb_op_res_unit_trace(unsigned long long* d_trace) {
+    res_unit_set_trace(d_trace);
+    return 0;
+}
+int fsb_res_unit(const void* d_a, const void* d_x, int B, int T, int C, int dilation, const void* d_w7,
+                 const float* d_b7, const float* d_alpha1, const float* d_inv1, const void* d_w1, const float* d_b1,
+                 void* d_out0, void* d_out1, const float* d_alpha_n, const float* d_inv_n, void* stream) {
+    FSB_TRY(gemm_init());
+    return res_unit_run(d_a, d_x, B, T, C, dilation, d_w7, d_b7, d_alpha1, d_inv1, d_w1, d_b1, d_out0, d_out1, d_alpha_n,
+                        d_inv_n, reinterpret_cast<cudaStream_t>(stream));
+}
+
 // Same GEMM, LM-style: fp32 results (one partial) for the transformer glue kernels below.
 //   ws[row][n] = sum_k x[row][k] * w[n][k]      x bf16 [rows, K], w bf16 [N, K]
 int fsb_linear_f32(const void* d_x, int rows, int K, const void* d_w, int N, float* d_ws, void* stream) {

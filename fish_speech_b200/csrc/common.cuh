@@ -210,6 +210,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
         : "memory");
 }
 
+// TMA store of a {64, rows, 1} box from shared memory (SWIZZLE_128B tile) to global memory; rows / columns outside
+// the tensor are clipped.  Part of the calling thread's current bulk async-group.
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 // TMA prefetch of a tile into L2 only (no shared memory, no barrier).
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));

@@ -91,4 +91,13 @@ int gemm_init();  // set kernel attributes (idempotent)
 // 3-D {k, rows, batch} bf16 tensor map with the 128-byte swizzle and a {64, box_rows, 1} box.
 int gemm_make_tmap(CUtensorMap* tm, const GemmOperand& op, int box_rows);
 
+// csrc/codec_resunit.cu: a whole decoder ResidualUnit (modded_dac.py:599-620) as one kernel. d_a = Snake-activated
+// input, d_x = raw residual stream, both bf16 [B][T][C]; w7 = [C][7][pad64(C)], w1 = [C][pad64(C)] bf16; out0 (raw, may
+// alias d_x, may be null) and out1 = Snake_next(result) (must not alias d_a).
+bool res_unit_supported(int C);
+void res_unit_set_trace(unsigned long long* d_trace);  // diagnostics: [64][6] stamps of CTA 0 (null = off)
+int res_unit_run(const void* d_a, const void* d_x, int B, int T, int C, int dilation, const void* d_w7,
+                 const float* d_b7, const float* d_alpha1, const float* d_inv1, const void* d_w1, const float* d_b1,
+                 void* d_out0, void* d_out1, const float* d_alpha_n, const float* d_inv_n, cudaStream_t st);
+
 }  // namespace fsb

@@ -118,6 +118,8 @@ class DAC:
         self._graphs: dict = {}   # (B, S, T) -> (CUDAGraph, static index buffer, static waveform) of from_indices
         self._graph_seen: dict = {}
         self._use_graphs = os.environ.get("FSB_CODEC_GRAPH", "1") != "0"
+        # decoder ResidualUnits as one kernel each (csrc/codec_resunit.cu); 0 = two conv GEMM launches per unit
+        self._fused_units = os.environ.get("FSB_FUSED_RESUNIT", "1") != "0"
         self._lock = threading.RLock()
         self._rope: dict = {}
         self._sd = {k: v.detach().float() for k, v in state_dict.items()}  # folded on the device they live on
@@ -240,7 +242,7 @@ class DAC:
 
     def _res_unit(self, prefix: str, dilation: int) -> dict:
         return dict(s0=self._snake(f"{prefix}.block.0"), c7=self._conv(f"{prefix}.block.1.conv", dilation=dilation),
-                    s1=self._snake(f"{prefix}.block.2"), c1=self._conv(f"{prefix}.block.3.conv"))
+                    s1=self._snake(f"{prefix}.block.2"), c1=self._conv(f"{prefix}.block.3.conv"), dil=dilation)
 
     def _vq_tables(self, prefix: str):
         """out_proj(codebook) tables (fp32 [size, D]) for decode, and in_proj / normalised codebook for encode."""
@@ -490,6 +492,11 @@ class DAC:
             buf[: B * Tc * D].view(B, Tc, D).copy_(z.to(self._device).transpose(1, 2))
             return self._decoder(buf, B, Tc).view(B, 1, -1)
 
+    def _unit_is_fusable(self, ru: dict, c: int) -> bool:
+        c7, c1 = ru["c7"], ru["c1"]
+        return (self._fused_units and c7.taps == 7 and c1.taps == 1 and c7.bias is not None and c1.bias is not None
+                and c7.kpad == _pad64(c) and c1.kpad == _pad64(c) and bool(self.lib.fsb_res_unit_supported(c)))
+
     def _decoder(self, z: torch.Tensor, B: int, T: int) -> torch.Tensor:
         """Decoder.forward (modded_dac.py:760-801) on z = flat [B][T][latent] bf16."""
         cfg = self.cfg
@@ -520,7 +527,6 @@ class DAC:
             a = a2
             for j, ru in enumerate(blk["res"]):
                 m = take()
-                self._gemm(ru["c7"], bufs[a], B, Tc, cout, Tc, out1=bufs[m], snake=ru["s1"])
                 last_unit = j == 2
                 if not last_unit:
                     nxt = blk["res"][j + 1]["s0"]
@@ -529,6 +535,19 @@ class DAC:
                 else:
                     nxt = self.dec_out_snake
                 keep_raw = not last_unit
+                if self._unit_is_fusable(ru, cout):
+                    # Snake -> conv7 -> Snake -> conv1 -> + x in one kernel; the activated result goes to the spare buffer
+                    # (neighbouring tiles still read their halo from bufs[a])
+                    c7, c1 = ru["c7"], ru["c1"]
+                    _lib.check(self.lib.fsb_res_unit(
+                        bufs[a].data_ptr(), bufs[x].data_ptr(), B, Tc, cout, ru["dil"], c7.w.data_ptr(), c7.bias.data_ptr(),
+                        ru["s1"].alpha.data_ptr(), ru["s1"].inv.data_ptr(), c1.w.data_ptr(), c1.bias.data_ptr(),
+                        bufs[x].data_ptr() if keep_raw else None, bufs[m].data_ptr(), nxt.alpha.data_ptr(),
+                        nxt.inv.data_ptr(), _stream()))
+                    free.append(a)
+                    a = m
+                    continue
+                self._gemm(ru["c7"], bufs[a], B, Tc, cout, Tc, out1=bufs[m], snake=ru["s1"])
                 self._gemm(ru["c1"], bufs[m], B, Tc, cout, Tc, out0=bufs[x] if keep_raw else None, out1=bufs[a],
                            snake=nxt, resid=bufs[x])
                 free.append(m)

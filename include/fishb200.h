@@ -222,6 +222,14 @@ int fsb_first_conv(const float* d_wav, const float* d_w, const float* d_bias, co
                    const float* d_inv_alpha, int B, int T, int C, int K, void* d_raw, void* d_act, void* stream);
 int fsb_snake(const void* d_x, const float* d_alpha, const float* d_inv_alpha, long long n, int C, void* d_y,
               void* stream);
+/* One decoder ResidualUnit -- y = x + conv1(snake_1(conv7_dilated(a))), a = snake_0(x) -- as ONE kernel (dac
+ * ResidualUnit, modded_dac.py:599-620 causal variant): the intermediate stays in shared memory. d_a / d_x bf16
+ * [B][T][C]; d_w7 [C][7][pad64(C)], d_w1 [C][pad64(C)] bf16 (the packing of fsb_conv_gemm); out0 = y (may alias d_x,
+ * may be NULL), out1 = snake_next(y) (must not alias d_a). C in {96, 192, 384} (fsb_res_unit_supported). */
+int fsb_res_unit_supported(int C);
+int fsb_res_unit(const void* d_a, const void* d_x, int B, int T, int C, int dilation, const void* d_w7,
+                 const float* d_b7, const float* d_alpha1, const float* d_inv1, const void* d_w1, const float* d_b1,
+                 void* d_out0, void* d_out1, const float* d_alpha_n, const float* d_inv_n, void* stream);
 /* 1 semantic + n residual vector-quantiser stages per latent frame (rvq.py:304-317, dac VectorQuantize). */
 int fsb_vq_encode(const void* d_z, const float* d_in_w, const float* d_in_b, const float* d_cbn,
                   const int32_t* d_cb_off, const int32_t* d_sizes, const float* const* d_tabs, int S, int cd, int B,
@@ -248,6 +256,9 @@ int fsb_op_gemm(const void* d_a, const void* d_b, float* d_out, int m, int n, in
 /* Attention keeps one fp32 score per position and head in shared memory; contexts longer than the buffer are walked
  * in chunks, bit-identically (csrc/lm_kernels.cu attend()).  positions > 0 forces a smaller chunk; 0 = automatic. */
 int fsb_op_attn_score_chunk(int positions);
+/* Diagnostics of fsb_res_unit: d_trace [64][6] globaltimer stamps of CTA 0's first tiles = {epilogue idle, conv7
+ * accumulator ready, h written, conv1 accumulator ready, outputs staged, stores issued}; NULL switches it off. */
+int fsb_op_res_unit_trace(unsigned long long* d_trace);
 
 #ifdef __cplusplus
 }

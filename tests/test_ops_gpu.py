@@ -196,3 +196,65 @@ def test_attention_past_the_score_buffer_is_chunked_bit_identically(H, Hkv, Dh):
         ref = torch.einsum("hs,hsd->hd", torch.softmax(s, -1), vv[:, :p + 1]).reshape(-1)
         err = (auto[i].float() - ref).abs().max().item()
         assert err <= 2 ** -7 * ref.abs().max().item() + 1e-3, (p, err)
+
+
+@pytest.mark.parametrize("C,dil,B,T", [(96, 1, 2, 300), (192, 3, 1, 517), (192, 9, 2, 128), (384, 9, 2, 260), (96, 9, 1, 40)])
+def test_fused_residual_unit_equals_two_conv_launches(C, dil, B, T):
+    """csrc/codec_resunit.cu (Snake -> dilated conv7 -> Snake -> conv1 -> + x in one kernel, the intermediate in shared
+    memory) against the same unit as two fsb_conv_gemm launches: identical bits (same MMA order, same rounding points),
+    and both against fp32 torch (modded_dac.py:599-620 with the causal pad of :546-552)."""
+    _l, L = _lib()
+    import ctypes as Ct
+    g = torch.Generator().manual_seed(C + dil + T)
+    cp = (C + 63) // 64 * 64
+    x = torch.randn(B, T, C, generator=g).bfloat16()
+    a0 = torch.rand(C, generator=g) + 0.5
+    a1 = torch.rand(C, generator=g) + 0.5
+    an = torch.rand(C, generator=g) + 0.5
+    snake = lambda v, al: v + (al + 1e-9).reciprocal() * torch.sin(al * v) ** 2
+    a = snake(x.float(), a0).bfloat16()
+    w7 = (torch.randn(C, C, 7, generator=g) * (7 * C) ** -0.5).bfloat16()
+    w1 = (torch.randn(C, C, 1, generator=g) * C ** -0.5).bfloat16()
+    b7 = torch.randn(C, generator=g) * 0.1
+    b1 = torch.randn(C, generator=g) * 0.1
+    pack = lambda w: torch.nn.functional.pad(w.permute(0, 2, 1).float(), (0, cp - C)).reshape(C, -1).bfloat16().cuda()
+    dw7, dw1 = pack(w7), pack(w1)
+    d = lambda t: t.cuda()
+    da, dx = d(a), d(x)
+    db7, db1 = d(b7), d(b1)
+    al1, iv1, aln, ivn = d(a1), d((a1 + 1e-9).reciprocal()), d(an), d((an + 1e-9).reciprocal())
+    # two launches (the existing path)
+    h = torch.empty_like(da)
+    y0, y1 = torch.empty_like(dx), torch.empty_like(dx)
+    sh7 = (Ct.c_int * 7)(*[-(6 - j) * dil for j in range(7)])
+    sh1 = (Ct.c_int * 1)(0)
+    _l.check(L.fsb_conv_gemm(da.data_ptr(), B, T, C, C, T * C, dw7.data_ptr(), C, 7, cp, sh7, T, db7.data_ptr(), None, None,
+                             0, None, h.data_ptr(), al1.data_ptr(), iv1.data_ptr(), 0, _st()))
+    _l.check(L.fsb_conv_gemm(h.data_ptr(), B, T, C, C, T * C, dw1.data_ptr(), C, 1, cp, sh1, T, db1.data_ptr(), None,
+                             dx.data_ptr(), 0, y0.data_ptr(), y1.data_ptr(), aln.data_ptr(), ivn.data_ptr(), 0, _st()))
+    # one kernel
+    f0, f1 = torch.empty_like(dx), torch.empty_like(dx)
+    assert L.fsb_res_unit_supported(C) == 1
+    _l.check(L.fsb_res_unit(da.data_ptr(), dx.data_ptr(), B, T, C, dil, dw7.data_ptr(), db7.data_ptr(), al1.data_ptr(),
+                            iv1.data_ptr(), dw1.data_ptr(), db1.data_ptr(), f0.data_ptr(), f1.data_ptr(), aln.data_ptr(),
+                            ivn.data_ptr(), _st()))
+    torch.cuda.synchronize()
+    assert torch.equal(f0, y0), (f0.float() - y0.float()).abs().max()
+    assert torch.equal(f1, y1), (f1.float() - y1.float()).abs().max()
+    # in place over x, raw output dropped
+    x2 = dx.clone()
+    f2 = torch.empty_like(dx)
+    _l.check(L.fsb_res_unit(da.data_ptr(), x2.data_ptr(), B, T, C, dil, dw7.data_ptr(), db7.data_ptr(), al1.data_ptr(),
+                            iv1.data_ptr(), dw1.data_ptr(), db1.data_ptr(), x2.data_ptr(), f2.data_ptr(), aln.data_ptr(),
+                            ivn.data_ptr(), _st()))
+    torch.cuda.synchronize()
+    assert torch.equal(x2, y0) and torch.equal(f2, y1)
+    # fp32 reference
+    xin = torch.nn.functional.pad(a.float().transpose(1, 2), (6 * dil, 0))
+    hh = torch.nn.functional.conv1d(xin, w7.float(), b7, dilation=dil)
+    hh = snake(hh.transpose(1, 2), a1).bfloat16().float().transpose(1, 2)
+    yy = torch.nn.functional.conv1d(hh, w1.float(), b1).transpose(1, 2) + x.float()
+    err = (f0.cpu().float() - yy).abs().max().item()
+    assert err <= 2 ** -6 * yy.abs().max().item() + 2e-2, err
+    err1 = (f1.cpu().float() - snake(yy, an)).abs().max().item()
+    assert err1 <= 2 ** -5 * snake(yy, an).abs().max().item() + 3e-2, err1
