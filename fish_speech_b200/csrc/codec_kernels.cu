@@ -84,33 +84,64 @@ dwconv_ln_kernel(const bf16* __restrict__ x, const float* __restrict__ w /*[C][K
 
 // ------------------------------------------------------------------------------------------------
 // wav[b][t] = tanh(bias + sum_{j<K} sum_c w[j][c] * a[b][t-(K-1)+j][c])   (a already Snake-activated)
+// One CTA = kFcTile consecutive time steps: the activation rows (with the K-1 row halo) are fetched with 16-byte
+// loads and kept as bf16 pairs in shared memory (row stride C/2 + 1 words: conflict-free for threads on consecutive
+// rows); each thread produces kFcPer outputs kFcThreads rows apart, so one weight read serves kFcPer FMAs.
 constexpr int kFcThreads = 128;
+constexpr int kFcPer = 2;
+constexpr int kFcTile = kFcThreads * kFcPer;
 __global__ void __launch_bounds__(kFcThreads)
 final_conv_tanh_kernel(const bf16* __restrict__ a, const float* __restrict__ w /*[K][C]*/, float bias, int T, int C,
                        int K, float* __restrict__ wav) {
     extern __shared__ float fsm[];
-    float* ws = fsm;           // [K*C]
-    float* xs = fsm + K * C;   // [(kFcThreads+K-1)][C+1]
+    float* ws = fsm;                                             // [K*C]
+    uint32_t* xs = reinterpret_cast<uint32_t*>(fsm + K * C);     // [kFcTile + K - 1][C/2 + 1] bf16 pairs
     pdl_launch_dependents();
     for (int e = threadIdx.x; e < K * C; e += kFcThreads) ws[e] = w[e];
     pdl_wait();
-    const int b = blockIdx.y, t0 = blockIdx.x * kFcThreads;
-    const int rows = kFcThreads + K - 1, ld = C + 1;
-    for (int e = threadIdx.x; e < rows * C; e += kFcThreads) {
-        const int r = e / C, c = e - r * C;
-        const int tt = t0 - (K - 1) + r;
-        xs[r * ld + c] = (tt >= 0 && tt < T) ? bf2f(a[(static_cast<size_t>(b) * T + tt) * C + c]) : 0.f;
+    const int b = blockIdx.y, t0 = blockIdx.x * kFcTile;
+    const int rows = kFcTile + K - 1, ldw = C / 2 + 1, vpr = C / 8;  // 16-byte vectors per row
+    if ((C & 7) == 0) {
+        for (int e = threadIdx.x; e < rows * vpr; e += kFcThreads) {
+            const int r = e / vpr, v = e - r * vpr;
+            const int tt = t0 - (K - 1) + r;
+            uint4 u = make_uint4(0, 0, 0, 0);
+            if (tt >= 0 && tt < T) u = *reinterpret_cast<const uint4*>(a + (static_cast<size_t>(b) * T + tt) * C + v * 8);
+            uint32_t* d = xs + r * ldw + v * 4;
+            d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+        }
+    } else {  // narrow test geometries: one bf16 pair per load
+        for (int e = threadIdx.x; e < rows * (C / 2); e += kFcThreads) {
+            const int r = e / (C / 2), v = e - r * (C / 2);
+            const int tt = t0 - (K - 1) + r;
+            uint32_t u = 0;
+            if (tt >= 0 && tt < T) u = *reinterpret_cast<const uint32_t*>(a + (static_cast<size_t>(b) * T + tt) * C + v * 2);
+            xs[r * ldw + v] = u;
+        }
     }
     __syncthreads();
-    const int t = t0 + threadIdx.x;
-    if (t >= T) return;
-    float acc = bias;
+    float acc[kFcPer];
+#pragma unroll
+    for (int o = 0; o < kFcPer; ++o) acc[o] = bias;
     for (int j = 0; j < K; ++j) {
-        const float* xr = xs + (threadIdx.x + j) * ld;
-        const float* wr = ws + j * C;
-        for (int c = 0; c < C; ++c) acc += wr[c] * xr[c];
+        const float2* wr = reinterpret_cast<const float2*>(ws + j * C);
+        const uint32_t* xr = xs + (threadIdx.x + j) * ldw;
+#pragma unroll 8
+        for (int cw = 0; cw < C / 2; ++cw) {
+            const float2 wv = wr[cw];
+#pragma unroll
+            for (int o = 0; o < kFcPer; ++o) {
+                const uint32_t x2 = xr[o * kFcThreads * ldw + cw];
+                acc[o] = fmaf(wv.x, bf_lo(x2), acc[o]);
+                acc[o] = fmaf(wv.y, bf_hi(x2), acc[o]);
+            }
+        }
     }
-    wav[static_cast<size_t>(b) * T + t] = tanhf(acc);
+#pragma unroll
+    for (int o = 0; o < kFcPer; ++o) {
+        const int t = t0 + o * kFcThreads + threadIdx.x;
+        if (t < T) wav[static_cast<size_t>(b) * T + t] = tanhf(acc[o]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -397,14 +428,14 @@ int fsb_dwconv_ln(const void* d_x, const float* d_w, const float* d_bias, const 
 int fsb_final_conv_tanh(const void* d_a, const float* d_w, float bias, int B, int T, int C, int K, float* d_wav,
                         void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const size_t smem = (static_cast<size_t>(K) * C + static_cast<size_t>(kFcThreads + K - 1) * (C + 1)) * sizeof(float);
-    FSB_CHECK(smem <= 200 * 1024, "final_conv: C=%d too large", C);
+    const size_t smem = (static_cast<size_t>(K) * C + static_cast<size_t>(kFcTile + K - 1) * (C / 2 + 1)) * sizeof(float);
+    FSB_CHECK(smem <= 200 * 1024 && (C & 1) == 0, "final_conv: C=%d not supported", C);
     static bool attr = false;
     if (!attr) {
         FSB_CUDA(cudaFuncSetAttribute(final_conv_tanh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    FSB_LAUNCH(final_conv_tanh_kernel, dim3(cdiv(T, kFcThreads), B), dim3(kFcThreads), smem, st,
+    FSB_LAUNCH(final_conv_tanh_kernel, dim3(cdiv(T, kFcTile), B), dim3(kFcThreads), smem, st,
                reinterpret_cast<const bf16*>(d_a), d_w, bias, T, C, K, d_wav);
     return 0;
 }
@@ -493,6 +524,10 @@ int fsb_window_attn(const void* d_q, const void* d_k, const void* d_v, const int
 
 int fsb_op_attn_score_chunk(int positions) {
     attn_set_score_chunk(positions);
+    return 0;
+}
+int fsb_op_attn_per_row(int on) {
+    attn_force_per_row(on != 0);
     return 0;
 }
 

@@ -275,6 +275,73 @@ __global__ void qkv_prep_kernel(QkvPrepArgs a) {
     }
 }
 
+// The same per (row, head) work with one CTA per row: a warp takes whole heads (lane = rotary pair, two pairs per lane
+// at head_dim 128), so the per-head norm is a warp reduction and a row costs one CTA of 8 warps instead of H + 2 Hkv
+// CTAs of Dh / 2 threads (393 216 one-warp CTAs per codec transformer layer at 32 x 256 frames).
+constexpr int kQkvRowThreads = 256;
+template <int DH>
+__global__ void __launch_bounds__(kQkvRowThreads) qkv_prep_row_kernel(QkvPrepArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int PPL = DH / 64;  // rotary pairs per lane
+    const int row = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pos = a.row_pos[row];
+    const int b = a.row_seq[row];
+    const int NH = a.H + 2 * a.Hkv;
+    for (int head = warp; head < NH; head += kQkvRowThreads / 32) {
+        const int kind = head < a.H ? 0 : (head < a.H + a.Hkv ? 1 : 2);  // q, k, v
+        const __nv_bfloat16* nw = kind == 0 ? a.q_norm : (kind == 1 ? a.k_norm : nullptr);
+        float v0[PPL], v1[PPL];
+        float ss = 0.f;
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+            const int t = lane + 32 * u;
+            const int f0 = head * DH + 2 * t;
+            const float2 y2 = *reinterpret_cast<const float2*>(a.y + static_cast<size_t>(row) * a.ld + f0);
+            v0[u] = y2.x;
+            v1[u] = y2.y;
+            if (a.bias) {
+                v0[u] += bf2f(a.bias[f0]);
+                v1[u] += bf2f(a.bias[f0 + 1]);
+            }
+            v0[u] = rbf(v0[u]);
+            v1[u] = rbf(v1[u]);
+            ss += v0[u] * v0[u] + v1[u] * v1[u];
+        }
+        if (nw != nullptr) {
+            // nn.RMSNorm(head_dim): fp32 math, weight multiply included, ONE rounding
+            const float r = rsqrtf(warp_sum(ss) / static_cast<float>(DH) + a.eps);
+#pragma unroll
+            for (int u = 0; u < PPL; ++u) {
+                const int t = lane + 32 * u;
+                v0[u] = rbf(v0[u] * r * bf2f(nw[2 * t]));
+                v1[u] = rbf(v1[u] * r * bf2f(nw[2 * t + 1]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+            const int t = lane + 32 * u;
+            if (kind != 2) {
+                const uint32_t cs = *reinterpret_cast<const uint32_t*>(a.freqs + (static_cast<size_t>(max(pos, 0)) * (DH / 2) + t) * 2);
+                const float c = bf_lo(cs), sn = bf_hi(cs);
+                const float o0 = __fsub_rn(__fmul_rn(v0[u], c), __fmul_rn(v1[u], sn));
+                const float o1 = __fadd_rn(__fmul_rn(v1[u], c), __fmul_rn(v0[u], sn));
+                v0[u] = rbf(o0);
+                v1[u] = rbf(o1);
+            }
+            const uint32_t packed = pack_bf2(v0[u], v1[u]);
+            if (kind == 0) {
+                reinterpret_cast<uint32_t*>(a.q + (static_cast<size_t>(row) * a.H + head) * DH)[t] = packed;
+            } else if (pos >= 0 && pos < a.S) {
+                const int g = kind == 1 ? head - a.H : head - a.H - a.Hkv;
+                __nv_bfloat16* cache = kind == 1 ? a.kcache : a.vcache;
+                reinterpret_cast<uint32_t*>(cache + ((static_cast<size_t>(b) * a.Hkv + g) * a.S + pos) * DH)[t] = packed;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // length-aware GQA attention over the KV cache (one query token per CTA, all G heads of a KV group)
 // ------------------------------------------------------------------------------------------------
@@ -953,14 +1020,18 @@ int launch_qkv_prep(const QkvPrepArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
     FSB_CHECK(a.Dh % 64 == 0 && a.Dh <= 256, "qkv_prep: head_dim %d unsupported", a.Dh);
     FSB_CHECK((a.ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 7) == 0, "qkv_prep: misaligned GEMM result");
-    FSB_LAUNCH(qkv_prep_kernel, dim3(a.rows, a.H + 2 * a.Hkv), dim3(a.Dh / 2), 0, st, a);
+    if (a.Dh == 64) FSB_LAUNCH(qkv_prep_row_kernel<64>, dim3(a.rows), dim3(kQkvRowThreads), 0, st, a);
+    else if (a.Dh == 128) FSB_LAUNCH(qkv_prep_row_kernel<128>, dim3(a.rows), dim3(kQkvRowThreads), 0, st, a);
+    else FSB_LAUNCH(qkv_prep_kernel, dim3(a.rows, a.H + 2 * a.Hkv), dim3(a.Dh / 2), 0, st, a);
     return 0;
 }
 
 // Score-buffer positions per head for a context bound of `need`: rounded up to a multiple of 32 and cut to what fits
 // 200 KB of shared memory (a longer context is walked in chunks, see attend()).  g_attn_chunk (tests) forces a chunk.
 static int g_attn_chunk = 0;
+static bool g_attn_per_row = false;  // tests: launch_attn uses the per-row kernel (the decode kernel's attention core)
 void attn_set_score_chunk(int positions) { g_attn_chunk = positions > 0 ? (positions + 31) / 32 * 32 : 0; }
+void attn_force_per_row(bool on) { g_attn_per_row = on; }
 template <int DH, int G>
 static size_t attn_smem_bytes(int lcap) {
     return (static_cast<size_t>(G) * DH + static_cast<size_t>(G) * lcap + static_cast<size_t>(kAttnWarps) * G * DH) *
@@ -1025,6 +1096,9 @@ int launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st) {
 
 int launch_attn(const AttnArgs& a, cudaStream_t st) {
     if (a.rows <= 0) return 0;
+    // one kernel whatever the number of rows: a sequence must get the same bits alone, in a batch or in pieces
+    static const bool tile_on = [] { const char* e = getenv("FSB_ATTN_TILE"); return !(e && e[0] == '0'); }();
+    if (tile_on && !g_attn_per_row && attn_tile_supported(a)) return launch_attn_tile(a, st);
     const int G = a.H / a.Hkv;
     FSB_CHECK(a.H % a.Hkv == 0, "attention: H %% Hkv != 0");
 #define FSB_ATTN_CASE(DH_, G_) \

@@ -94,8 +94,13 @@ struct AttnArgs {
     int bf16_math;
 };
 int launch_attn(const AttnArgs& a, cudaStream_t st);
+// csrc/attn_tile.cu: 64 rows of one head per CTA, K/V tiles staged once, mma.sync tensor cores, online softmax; what
+// launch_attn uses for >= 64 rows (prefill, codec transformer).  FSB_ATTN_TILE=0 keeps the per-row kernel.
+bool attn_tile_supported(const AttnArgs& a);
+int launch_attn_tile(const AttnArgs& a, cudaStream_t st);
 int attn_init();  // set kernel attributes (idempotent)
 void attn_set_score_chunk(int positions);  // tests: force the score-buffer chunk (0 = automatic)
+void attn_force_per_row(bool on);          // tests: launch_attn runs the per-row kernel instead of the tiled one
 
 // Decode-step attention: the consumer of the qkv step GEMM. One CTA per (batch row, KV group) first finishes that
 // GEMM for its own (G + 2) heads -- slot-ordered sum of the stream-K partials, bias, per-head nn.RMSNorm, interleaved

@@ -256,6 +256,9 @@ int fsb_op_gemm(const void* d_a, const void* d_b, float* d_out, int m, int n, in
 /* Attention keeps one fp32 score per position and head in shared memory; contexts longer than the buffer are walked
  * in chunks, bit-identically (csrc/lm_kernels.cu attend()).  positions > 0 forces a smaller chunk; 0 = automatic. */
 int fsb_op_attn_score_chunk(int positions);
+/* fsb_window_attn normally runs the tiled tensor-core kernel (csrc/attn_tile.cu); on != 0 makes it run the per-row
+ * kernel, whose attention core is the one of the decode step (what the chunking test above exercises). */
+int fsb_op_attn_per_row(int on);
 /* Diagnostics of fsb_res_unit: d_trace [64][6] globaltimer stamps of CTA 0's first tiles = {epilogue idle, conv7
  * accumulator ready, h written, conv1 accumulator ready, outputs staged, stores issued}; NULL switches it off. */
 int fsb_op_res_unit_trace(unsigned long long* d_trace);

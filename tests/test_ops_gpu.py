@@ -178,6 +178,7 @@ def test_attention_past_the_score_buffer_is_chunked_bit_identically(H, Hkv, Dh):
 
     def run(chunk):
         _l.check(L.fsb_op_attn_score_chunk(chunk))
+        _l.check(L.fsb_op_attn_per_row(1))  # the per-row kernel = the decode step's attention core
         out = torch.empty(rows, H * Dh, dtype=torch.bfloat16, device="cuda")
         try:
             _l.check(L.fsb_window_attn(dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dseq.data_ptr(), dpos.data_ptr(), rows,
@@ -185,6 +186,7 @@ def test_attention_past_the_score_buffer_is_chunked_bit_identically(H, Hkv, Dh):
             torch.cuda.synchronize()
         finally:
             L.fsb_op_attn_score_chunk(0)
+            L.fsb_op_attn_per_row(0)
         return out.cpu()
 
     auto = run(0)
@@ -258,3 +260,47 @@ def test_fused_residual_unit_equals_two_conv_launches(C, dil, B, T):
     assert err <= 2 ** -6 * yy.abs().max().item() + 2e-2, err
     err1 = (f1.cpu().float() - snake(yy, an)).abs().max().item()
     assert err1 <= 2 ** -5 * snake(yy, an).abs().max().item() + 3e-2, err1
+
+
+@pytest.mark.parametrize("H,Hkv,Dh,window", [(8, 2, 128, 0), (16, 16, 64, 128)])
+def test_tiled_attention_matches_sdpa_and_is_grouping_independent(H, Hkv, Dh, window):
+    """csrc/attn_tile.cu (64 rows per CTA, mma.sync, online softmax) on ragged multi-sequence row sets: against fp32
+    SDPA, and bit-identical whichever rows share a tile (the rows of a prompt prefilled in one pass, in chunks, or next
+    to other sequences) -- what prefix KV reuse relies on."""
+    _l, L = _lib()
+    S = 700
+    lens = [333, 70, 1, 200]
+    B = len(lens)
+    g = torch.Generator().manual_seed(H + window)
+    k = torch.randn(B, Hkv, S, Dh, generator=g).bfloat16()
+    v = torch.randn(B, Hkv, S, Dh, generator=g).bfloat16()
+    seq = torch.cat([torch.full((n,), b, dtype=torch.int32) for b, n in enumerate(lens)])
+    pos = torch.cat([torch.arange(n, dtype=torch.int32) for n in lens])
+    rows = seq.numel()
+    q = (torch.randn(rows, H, Dh, generator=g) * 1.5).bfloat16()
+    dk, dv = k.cuda(), v.cuda()
+
+    def run(idx):
+        idx = torch.as_tensor(idx, dtype=torch.long)
+        dq, dseq, dpos = q[idx].cuda().contiguous(), seq[idx].cuda(), pos[idx].cuda()
+        out = torch.empty(idx.numel(), H * Dh, dtype=torch.bfloat16, device="cuda")
+        _l.check(L.fsb_window_attn(dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dseq.data_ptr(), dpos.data_ptr(),
+                                   idx.numel(), H, Hkv, Dh, S, window, out.data_ptr(), _st()))
+        torch.cuda.synchronize()
+        return out.cpu()
+
+    full = run(range(rows))
+    # sequence 0 alone from position 100 on (a later prefill chunk), and everything shifted by 7 rows (other tiling)
+    part = run(range(100, 333))
+    assert torch.equal(part, full[100:333])
+    shifted = run(list(range(7, rows)))
+    assert torch.equal(shifted, full[7:])
+    kk = k.float().repeat_interleave(H // Hkv, dim=1)
+    vv = v.float().repeat_interleave(H // Hkv, dim=1)
+    for r in (0, 1, 63, 64, 150, 332, 333, 402, 403, 404, rows - 1):
+        b, p = int(seq[r]), int(pos[r])
+        lo = max(0, p - window + 1) if window else 0
+        s = torch.einsum("hd,hsd->hs", q[r].float(), kk[b, :, lo:p + 1]) / Dh ** 0.5
+        ref = torch.einsum("hs,hsd->hd", torch.softmax(s, -1), vv[b, :, lo:p + 1]).reshape(-1)
+        err = (full[r].float() - ref).abs().max().item()
+        assert err <= 2 ** -7 * ref.abs().max().item() + 2e-3, (r, err)
