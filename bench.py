@@ -122,7 +122,7 @@ def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` capture (profiles/r02_step_gemm_ncu_full.json); None if no capture is committed."""
     try:
-        d = json.loads((ROOT / "profiles" / "r01_gemm32_ncu_full.json").read_text())
+        d = json.loads((ROOT / "profiles" / "r02_step_gemm_ncu_full.json").read_text())
         return d["avg_dram_bytes_per_launch"]
     except Exception:
         return None
