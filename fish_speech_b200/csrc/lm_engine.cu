@@ -45,6 +45,7 @@ struct StepLayer {
 };
 struct PrefillLayer {
     GemmPlan qkv, wo, w13, w2;
+    GemmPlan qkv_wide, w13_wide;  // the same GEMMs with 256-row tiles of the token rows (half the weight-tile traffic)
 };
 
 struct Stack {
@@ -131,7 +132,8 @@ int dalloc(fsb_lm* h, T** p, size_t count, const char* name = nullptr) {
 }
 
 // Prefill plan: A = weight [n_out, k] on the TMEM lanes, B = activations [rows, k], fp32 result ws[row][n_out].
-int make_prefill_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const bf16* act, int act_rows) {
+int make_prefill_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k, const bf16* act, int act_rows,
+                      int bn = 128) {
     memset(plan, 0, sizeof(*plan));
     GemmOperand A{w, k, n_out, 1, k, static_cast<long long>(n_out) * k};
     GemmOperand B{act, k, act_rows, 1, k, static_cast<long long>(act_rows) * k};
@@ -145,18 +147,27 @@ int make_prefill_plan(fsb_lm* h, GemmPlan* plan, const bf16* w, int n_out, int k
     p.mode = 0;
     p.ws = h->ws;
     p.ws_ld = n_out;
-    FSB_TRY(gemm_plan_init(plan, A, B, 128, 4, cdiv(n_out, 128), cdiv(act_rows, 128), 1));
+    FSB_TRY(gemm_plan_init(plan, A, B, bn, 4, cdiv(n_out, 128), cdiv(act_rows, bn), 1));
     p.rows_j = act_rows;
     p.ws_slot_stride = 0;
     FSB_CHECK(static_cast<size_t>(act_rows) * n_out <= h->ws_floats, "prefill workspace too small");
     return 0;
 }
 
+// 256-row tiles once enough token rows exist to fill the SMs with them: per output element the K loop is the same
+// sequence of MMAs, so the result does not depend on the tile width (chunked prefill == one pass stays bit-exact)
+int launch_rows_of(const GemmPlan& plan, const GemmPlan& wide, int rows, cudaStream_t st);
 int launch_rows_of(const GemmPlan& plan, int rows, cudaStream_t st) {
     GemmPlan q = plan;  // restrict the column tiles to the live rows
     q.grid.y = cdiv(rows, plan.bn);
     q.p.rows_j = rows;
     return gemm_launch(q, st);
+}
+
+int launch_rows_of(const GemmPlan& plan, const GemmPlan& wide, int rows, cudaStream_t st) {
+    static const bool on = [] { const char* e = getenv("FSB_PREFILL_WIDE"); return !(e && e[0] == '0'); }();
+    const long long tiles_wide = static_cast<long long>(wide.grid.x) * cdiv(rows, 256);
+    return (on && rows >= 512 && tiles_wide >= 296) ? launch_rows_of(wide, rows, st) : launch_rows_of(plan, rows, st);
 }
 
 // Step GEMM over the weight `w` [n_out, K]. act != null: operand X = act, used as it is; act == null: operand X = the
@@ -252,7 +263,7 @@ int run_stack_prefill(fsb_lm* h, Stack& s, int rows, const int* row_seq, const i
     for (int l = 0; l < s.nl; ++l) {
         const LayerW& w = s.w[l];
         PrefillLayer& P = s.pf[l];
-        FSB_TRY(launch_rows_of(P.qkv, rows, st));
+        FSB_TRY(launch_rows_of(P.qkv, P.qkv_wide, rows, st));
         QkvPrepArgs qa{};
         qa.y = h->ws; qa.ld = Nqkv;
         qa.bias = w.bqkv;
@@ -287,7 +298,7 @@ int run_stack_prefill(fsb_lm* h, Stack& s, int rows, const int* row_seq, const i
         r1.norm_w = w.ffn_norm; r1.n_out = h->xn_p;
         r1.rows = rows; r1.D = s.D; r1.eps = eps;
         FSB_TRY(launch_resid_norm(r1, st));
-        FSB_TRY(launch_rows_of(P.w13, rows, st));
+        FSB_TRY(launch_rows_of(P.w13, P.w13_wide, rows, st));
         SwigluArgs sa{};
         sa.y = h->ws; sa.ld = s.n13;
         sa.h = h->h_p; sa.rows = rows; sa.I = s.I;
@@ -606,6 +617,8 @@ int fsb_lm_create(const fsb_lm_config* cfg, const fsb_lm_weights* w, fsb_lm** ou
                 FSB_TRY(make_prefill_plan(h, &st.pf[l].qkv, lw.wqkv, Nqkv, st.D, h->xn_p, R));
                 FSB_TRY(make_prefill_plan(h, &st.pf[l].wo, lw.wo, st.D, st.H * st.Dh, h->attn_p, R));
                 FSB_TRY(make_prefill_plan(h, &st.pf[l].w13, lw.w13, st.n13, st.D, h->xn_p, R));
+                FSB_TRY(make_prefill_plan(h, &st.pf[l].qkv_wide, lw.wqkv, Nqkv, st.D, h->xn_p, R, 256));
+                FSB_TRY(make_prefill_plan(h, &st.pf[l].w13_wide, lw.w13, st.n13, st.D, h->xn_p, R, 256));
                 FSB_TRY(make_prefill_plan(h, &st.pf[l].w2, lw.w2, st.D, st.I, h->h_p, R));
             }
         }
@@ -639,7 +652,7 @@ void fsb_lm_destroy(fsb_lm* h) {
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     auto free_plans = [](Stack& st) {
         for (auto& p : st.dec) { step_plan_free(&p.qkv); step_plan_free(&p.wo); step_plan_free(&p.w13); step_plan_free(&p.w2); }
-        for (auto& p : st.pf) { gemm_plan_free(&p.qkv); gemm_plan_free(&p.wo); gemm_plan_free(&p.w13); gemm_plan_free(&p.w2); }
+        for (auto& p : st.pf) { gemm_plan_free(&p.qkv); gemm_plan_free(&p.wo); gemm_plan_free(&p.w13); gemm_plan_free(&p.w2); gemm_plan_free(&p.qkv_wide); gemm_plan_free(&p.w13_wide); }
     };
     free_plans(h->slow);
     free_plans(h->fast);

@@ -67,6 +67,28 @@ def test_decode_matches_oracle(tiny, B, T):
     assert s >= 30.0, f"decode SNR {s:.1f} dB"
 
 
+def test_decode_with_fused_residual_units_matches_oracle():
+    """Decoder blocks of 192 and 96 channels: their ResidualUnits run as ONE kernel each (csrc/codec_resunit.cu; the full
+    geometry's 384 / 192 / 96 blocks do): waveform vs the fp32 oracle, and identical bits with the fused kernel switched
+    off (two conv GEMM launches per unit)."""
+    import dataclasses
+    import os
+
+    cfg = dataclasses.replace(CO.tiny_config(), decoder_dim=384)
+    w = CO.make_weights(cfg, seed=5)
+    codes = rand_codes(cfg, 2, 37, 3)
+    ref = CO.from_indices(w, cfg, codes)
+    dac = build(cfg, w)
+    assert dac._fused_units and dac._unit_is_fusable(dac.dec_blocks[0]["res"][0], 192)
+    wav = dac.from_indices(codes.clone().cuda()).cpu()
+    assert snr_db(ref, wav) >= 30.0, f"SNR {snr_db(ref, wav):.1f} dB"
+    dac._fused_units = False
+    dac._graphs.clear()
+    dac._graph_seen.clear()
+    wav2 = dac.from_indices(codes.clone().cuda()).cpu()
+    assert torch.equal(wav, wav2), "fused ResidualUnit != two conv launches"
+
+
 def test_decode_stagewise(tiny):
     """Quantizer front half in isolation: latent z_up vs the oracle (localises errors)."""
     cfg, w, dac = tiny

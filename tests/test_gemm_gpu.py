@@ -50,3 +50,24 @@ def test_gemm_direct(m, n, k, bn):
 ])
 def test_gemm_streamk(m, n, k, ctas):
     _run(m, n, k, 32, ctas)
+
+
+def test_tile_width_does_not_change_the_bits():
+    """Prefill uses 256-row tiles of the token rows when there are enough of them and 128-row tiles otherwise
+    (csrc/lm_engine.cu launch_rows_of): per output element the K loop is the same MMA sequence, so the two give the same
+    bits -- what keeps chunked prefill, prefix reuse and batch invariance bit-exact."""
+    from fish_speech_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(5)
+    m, n, k = 640, 700, 2560
+    a = (torch.randn(m, k, generator=g) * 0.5).bfloat16().cuda()
+    b = (torch.randn(n, k, generator=g) * 0.5).bfloat16().cuda()
+    outs = []
+    for bn in (64, 128, 256):
+        out = torch.full((n, m), float("nan"), device="cuda", dtype=torch.float32)
+        _lib.check(L.fsb_op_gemm(a.data_ptr(), b.data_ptr(), out.data_ptr(), m, n, k, bn, 0,
+                                 torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])

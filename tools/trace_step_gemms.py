@@ -1,6 +1,7 @@
-"""Diagnostic: per-CTA timeline of the decode step GEMMs (include/fishb200.h fsb_lm_trace_step_gemms).
+"""Diagnostic: per-CTA timeline of the decode step GEMMs launched back to back, without the consumer kernels between them
+(include/fishb200.h fsb_lm_trace_step_gemms); tools/trace_frame.py is the in-frame version.
 
-    python tools/trace_step_gemms.py [--layers 4]      (FSB_FORCE_CTAS_PER_SM=2 to override the occupancy cap)
+    python tools/trace_step_gemms.py [--layers 4]
 """
 import argparse
 import ctypes as C
@@ -46,7 +47,7 @@ def main():
     names = ["qkv", "wo", "w13", "w2"]
     g = grid.value
     print(f"grid {g} CTAs; per launch: wall = last end - first start; medians over CTAs, microseconds")
-    print("launch  kind  wall   start_spread  prev_done  pro_done  x_ready  first_acc  end    rs_ready  first_norm")
+    print("launch  kind  wall   start_spread  wait_returned  first_acc  end    normalisers_ready  first_tile_normalised")
     prev_end = None
     for i in range(n):
         r = t[i, :g].double()
@@ -57,8 +58,8 @@ def main():
         wall = float(r[:, 5].max() - t0) / 1e3
         spread = float(r[:, 0].max() - t0) / 1e3
         gap = "" if prev_end is None else f" gap {float(t0 - prev_end) / 1e3:6.2f}"
-        print(f"{i:4d}  {names[i % 4]:4s} {wall:6.2f}  {spread:8.2f}  {med(1):8.2f}  {med(2):8.2f}  {med(3):8.2f}  {med(4):8.2f}  "
-              f"{med(5):6.2f}  {med(6):6.2f}  {med(7):6.2f}{gap}")
+        print(f"{i:4d}  {names[i % 4]:4s} {wall:6.2f}  {spread:8.2f}  {med(1):12.2f}  {med(4):8.2f}  {med(5):6.2f}  {med(6):12.2f}  "
+              f"{med(7):12.2f}{gap}")
         prev_end = r[:, 5].max()
 
 
