@@ -549,7 +549,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly ONE line, the JSON result: whatever NCCL prints while the communicator comes up (its
+        # version banner at NCCL_DEBUG=VERSION / INFO goes to stdout) is sent to stderr; NCCL's settings are not touched
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     cfg = s2pro_cfg()
     B, NF = args.batch, args.frames
     # N > 1: rank 0 synthesises the checkpoint, the other ranks receive it over NCCL (NVLink) -- the start-up path of a
