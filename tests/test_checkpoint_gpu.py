@@ -49,6 +49,46 @@ def test_init_model_from_checkpoint_dir_reproduces_reference_golden(tmp_path):
     assert torch.equal(seq, torch.from_numpy(z["ref_tokens"])[:, T:])
 
 
+@pytest.mark.parametrize("sharded", [True, False])
+def test_init_model_from_safetensors_with_hf_style_keys(tmp_path, sharded):
+    """llama.py:549-567: `model.safetensors.index.json` + shards (or one `model.safetensors`) whose keys carry the
+    released checkpoints' prefixes (`text_model.model.*`, `audio_decoder.*` -> `_remap_fish_qwen3_omni_keys`,
+    llama.py:229-246): same tokens as the reference golden."""
+    from safetensors.torch import save_file
+
+    from fish_speech_b200.models.text2semantic import inference as inf
+
+    cfg, w, z = load_golden(GOLD / "lm_tiny_greedy.npz")
+    conf = dataclasses.asdict(model_args(cfg))
+    conf["im_end_id"] = cfg.im_end_id
+    (tmp_path / "config.json").write_text(json.dumps(conf))
+
+    def hf_key(k):
+        if k.startswith("fast_"):
+            return "audio_decoder." + k[len("fast_"):]
+        if k.startswith("codebook_embeddings."):
+            return "audio_decoder." + k
+        return "text_model.model." + k
+
+    sd = {hf_key(k): v.contiguous() for k, v in w.items()}
+    if sharded:
+        keys = sorted(sd)
+        half = len(keys) // 2
+        parts = {"model-00001-of-00002.safetensors": keys[:half], "model-00002-of-00002.safetensors": keys[half:]}
+        for fn, ks in parts.items():
+            save_file({k: sd[k] for k in ks}, str(tmp_path / fn))
+        (tmp_path / "model.safetensors.index.json").write_text(
+            json.dumps({"metadata": {}, "weight_map": {k: fn for fn, ks in parts.items() for k in ks}}))
+    else:
+        save_file(sd, str(tmp_path / "model.safetensors"))
+    model, decode_one_token = inf.init_model(str(tmp_path), "cuda", torch.bfloat16, compile=False)
+    model.setup_caches(max_batch_size=1, max_seq_len=model.config.max_seq_len, dtype=torch.bfloat16)
+    got = inf.generate(model=model, prompt=torch.from_numpy(z["prompt"]).cuda(), max_new_tokens=int(z["new_frames"]),
+                       decode_one_token=decode_one_token, temperature=float(z["temperature"]), top_p=float(z["top_p"]),
+                       top_k=int(z["top_k"])).cpu()
+    assert torch.equal(got.to(torch.int32), torch.from_numpy(z["ref_tokens"]))
+
+
 def test_codec_load_model_from_checkpoint_file(tmp_path):
     from fish_speech_b200.models.dac import inference as dinf
     from tests.test_codec_gpu import build, rand_codes
