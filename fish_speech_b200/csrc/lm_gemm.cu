@@ -1,9 +1,9 @@
-// See lm_gemm.cuh.  CTA = 8 warps (6 when operand X needs no normalisation):
-//   warps 0-3  prologue (slot-ordered fix-up + epilogue of the PREVIOUS GEMM for this CTA's units, grid-wide arrival),
-//              then TMEM -> registers -> fp32 partial stores of this GEMM
+// See lm_gemm.cuh.  CTA = 10 warps (6 when operand X needs no normalisation):
+//   warps 0-3  TMEM -> registers -> fp32 partial stores of this GEMM
 //   warp  4    TMA producer (weights and operand X)
 //   warp  5    TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 6-7  operand-X normalisers (NORM == 1): RMSNorm of the TMA-delivered residual rows, in place in the ring
+//   warps 6-9  operand-X normalisers (NORM == 1): RMSNorm of the TMA-delivered residual rows, in place in the ring
+// step_finalize_kernel (the consumer-side finish of a GEMM: residual add / SwiGLU) lives here as well.
 #include "lm_gemm.cuh"
 #include "umma.cuh"
 
@@ -33,7 +33,7 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     return v;
 }
 
-// ---- prologue: one unit = rows [j0, j0 + R) x the 128 features of tile `tile` of the PREVIOUS GEMM's output;
+// ---- step_finalize: one unit = rows [j0, j0 + R) x the 128 features of tile `tile` of the PREVIOUS GEMM's output;
 // thread tid owns feature tile*128 + tid.  `red` = shared float[4][32]. ----
 
 // Per-row sum over the 128 features of the tile: result for row r in red[q*32 + r], q = 0..3 (one per warp).
@@ -134,8 +134,8 @@ __device__ __forceinline__ void pro_units(const StepGemmParams& p, int tid, floa
     }
 }
 
-// The prologue as a kernel of its own (one unit per CTA): used where the consumer of a GEMM is not a GEMM, and as the
-// alternative schedule (FSB_PROLOGUE=0) in which every step GEMM finds its operand complete.
+// step_finalize: finishes the GEMM that produced the next GEMM's operand (one unit = R batch rows x one 128-feature
+// tile per CTA); launched between the two GEMMs, so the consumer GEMM finds its operand complete.
 template <int PRO>
 __global__ void __launch_bounds__(kEpiThreads) step_finalize_kernel(const __grid_constant__ StepGemmParams p) {
     __shared__ float red[4 * 32];
@@ -171,7 +171,7 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(bar_gen + 24 * stages + 40);
     float* scratch = reinterpret_cast<float*>(bar_gen + scratch_off);
     float* r_s = scratch;       // [32] per-row rsqrt (normalisers)
-    float* red = scratch + 32;  // [4][32] cross-warp reductions (prologue)
+    float* red = scratch + 32;  // [4][32] spare
     uint4* normw_s = reinterpret_cast<uint4*>(bar_gen + scratch_off + kScratchBytes);  // [kblocks*8] norm weights
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -231,9 +231,8 @@ step_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                 }
-                // ... and the weight tiles after those go to L2: the HBM stream of this GEMM keeps running through the
-                // tail of the previous kernel, the prologue and the grid-wide arrival; the main loop then finds them
-                // on chip (126 MB of L2 hold a whole GEMM's weights)
+                // ... optionally (FSB_L2_PREFETCH, default 0: measured no gain, profiles/r02_l2_prefetch.md) the weight
+                // tiles after those are requested into L2
                 for (int q = 0; q < p.l2_prefetch && n < item_end; ++q) {
                     tma_prefetch_l2_3d(&tmA, kb * kBlockK, w.x * kBlockM, 0);
                     if (++kb >= w.z) {
