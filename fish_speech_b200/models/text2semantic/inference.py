@@ -503,6 +503,7 @@ def serve_requests(model, input_queue: "queue.Queue", max_slots: int, frames_per
         batcher = ContinuousBatcher(model, max_slots=max_slots, frames_per_poll=frames_per_poll)
     live = 0  # plans not yet exhausted
     waiting_queues: dict = {}  # id(plan) -> response queue of every plan that has a generate call in flight
+    streaming: set = set()  # id(plan) of requests that asked for partial codes (`stream_frames`)
     closing = False
 
     def advance(plan, response_queue, reply):
@@ -518,19 +519,26 @@ def serve_requests(model, input_queue: "queue.Queue", max_slots: int, frames_per
                     continue
                 if payload.get("audio_parts") is not None:
                     raise NotImplementedError("audio_parts is not supported (nor by the reference model)")
+                on_frames = None
+                if id(plan) in streaming:  # finished frames leave as "partial" responses, ahead of the chunk's "sample"
+                    def on_frames(r, codes, q=response_queue):
+                        q.put(WrappedGenerateResponse(status="success",
+                                                      response=GenerateResponse(action="partial", codes=codes)))
                 batcher.submit(SlotRequest(
                     prompt=payload["prompt"], max_new_tokens=payload["max_new_tokens"],
                     temperature=payload["temperature"], top_p=payload["top_p"], top_k=payload["top_k"],
-                    seed=_next_seed(model), reuse_prefix=bool(payload.get("reuse_prefix", False)),
+                    seed=_next_seed(model), reuse_prefix=bool(payload.get("reuse_prefix", False)), on_frames=on_frames,
                     on_done=lambda r, plan=plan, q=response_queue: advance(plan, q, r.result)))
                 waiting_queues[id(plan)] = response_queue
                 return
         except StopIteration:
             live -= 1
+            streaming.discard(id(plan))
         except Exception as e:
             logger.error(traceback.format_exc())
             response_queue.put(WrappedGenerateResponse(status="error", response=e))
             live -= 1
+            streaming.discard(id(plan))
 
     try:
         while True:
@@ -551,6 +559,8 @@ def serve_requests(model, input_queue: "queue.Queue", max_slots: int, frames_per
                     item.response_queue.put(WrappedGenerateResponse(status="error", response=e))
                     live -= 1
                     continue
+                if item.request.get("stream_frames", 0):
+                    streaming.add(id(plan))
                 advance(plan, item.response_queue, None)
             if live == 0 and closing:
                 return

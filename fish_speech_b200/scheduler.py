@@ -31,6 +31,9 @@ class SlotRequest:
     seed: int = 0
     reuse_prefix: bool = False  # prefill only the rows whose K/V no slot already holds (LmEngine.prefill_reusing)
     on_done: Optional[Callable[["SlotRequest"], None]] = None
+    # streaming: called after a poll with the codes [C, k] of frames that are final, in order; over the
+    # whole request exactly result[1:, T:-1] (what generate_long keeps, inference.py:708), before on_done
+    on_frames: Optional[Callable[["SlotRequest", torch.Tensor], None]] = None
     tag: object = None
     # filled by the batcher
     result: Optional[torch.Tensor] = None  # [C+1, T+n] like generate()
@@ -38,6 +41,7 @@ class SlotRequest:
     done: threading.Event = field(default_factory=threading.Event)
     slot: int = -1
     _limit: int = 0
+    _emitted: int = 0
 
 
 class ContinuousBatcher:
@@ -156,6 +160,15 @@ class ContinuousBatcher:
 
     def _retire(self) -> list[SlotRequest]:
         st = torch.stack([self._state.to(torch.int32), self._n_out]).cpu()  # one small D2H copy (synchronises)
+        for s, req in self.active.items():
+            # frames of a streaming request leave as soon as they are final: all but the newest one (the last frame of
+            # a request -- <|im_end|> or the one at the budget -- is never part of what generate_long keeps)
+            if req.on_frames is None:
+                continue
+            n = int(st[1, s])
+            if n - 1 > req._emitted:
+                req.on_frames(req, self._out[s, 1:, req._emitted: n - 1].cpu())
+                req._emitted = n - 1
         finished = []
         for s, req in list(self.active.items()):
             if int(st[0, s]) != 2:

@@ -579,3 +579,72 @@ def test_generate_long_plan_builds_growing_prompts_with_the_reference_frontend()
     assert kinds == ["sample"] * len(prompts) + ["next"]
     for i, r in enumerate(responses[:-1]):
         assert r.codes.shape == (10, 4 + i) and torch.equal(r.codes[:, 0], (torch.arange(10) + i + 1) % 1024)
+
+
+def test_continuous_batcher_streams_final_frames_per_request():
+    """SlotRequest.on_frames (SURVEY 8f.3 in the slot scheduler): after every poll a streaming request receives the codes
+    of the frames that are final -- all but its newest -- and over its lifetime exactly result[1:, T:-1], before on_done;
+    requests without the callback are untouched; two requests of different lengths stream independently."""
+    from fish_speech_b200.scheduler import ContinuousBatcher, SlotRequest
+
+    eng = _FakeEngine(slots=2, max_frames=32)
+    b = ContinuousBatcher(_SchedModel(eng), max_slots=2, frames_per_poll=4)
+    got = {0: [], 1: []}
+    order = []
+    mk = lambda i, n, stream: SlotRequest(
+        prompt=torch.full((3, 5), i, dtype=torch.long), max_new_tokens=n, tag=i,
+        on_frames=(lambda r, codes: (got[r.tag].append(codes.clone()), order.append(("frames", r.tag)))) if stream else None,
+        on_done=lambda r: order.append(("done", r.tag)))
+    r0, r1, r2 = mk(0, 11, True), mk(1, 6, True), mk(2, 7, False)
+    for r in (r0, r1, r2):
+        b.submit(r)
+    b.run()
+    for r in (r0, r1):
+        kept = r.result[1:, 5:-1]
+        cat = torch.cat(got[r.tag], dim=1)
+        assert torch.equal(cat.to(kept.dtype), kept), (r.tag, cat.shape, kept.shape)
+        assert len(got[r.tag]) >= 2 and all(c.device.type == "cpu" for c in got[r.tag])
+        assert order.index(("done", r.tag)) > max(i for i, e in enumerate(order) if e == ("frames", r.tag))
+    assert r2.result.shape[1] == 5 + 7 and ("frames", 2) not in order
+
+
+def test_slot_scheduler_worker_sends_partials_for_streaming_requests(monkeypatch):
+    """serve_requests with `stream_frames` in a request: "partial" responses (codes of final frames) arrive on that
+    request's queue ahead of each chunk's "sample" and add up to the sample's codes; other requests see none."""
+    import queue as Q
+
+    from fish_speech_b200.scheduler import ContinuousBatcher
+
+    def plan(*, model, text, **kw):
+        for c in range(2):
+            y = yield ("generate", dict(prompt=torch.full((3, 4), 1, dtype=torch.long), max_new_tokens=9 + c, audio_masks=None,
+                                        audio_parts=None, temperature=0.7, top_p=0.7, top_k=30))
+            yield ("response", inf.GenerateResponse(action="sample", codes=y[1:, 4:-1], text=f"{text}#{c}"))
+        yield ("response", inf.GenerateResponse(action="next"))
+
+    monkeypatch.setattr(inf, "_generate_long_plan", plan)
+    eng = _FakeEngine(slots=2, max_frames=32)
+    model = _SchedModel(eng)
+    model._philox_calls = 0
+    b = ContinuousBatcher(model, max_slots=2, frames_per_poll=4)
+    q, rs, rn = Q.Queue(), Q.Queue(), Q.Queue()
+    q.put(inf.GenerateRequest(request=dict(text="s", stream_frames=8), response_queue=rs))
+    q.put(inf.GenerateRequest(request=dict(text="n"), response_queue=rn))
+    q.put(None)
+    inf.serve_requests(model, q, 2, batcher=b)
+    items = []
+    while not rs.empty():
+        items.append(rs.get_nowait())
+    assert all(it.status == "success" for it in items)
+    acts = [it.response.action for it in items]
+    assert acts[-1] == "next" and acts.count("sample") == 2 and acts.count("partial") >= 2
+    i0 = acts.index("sample")
+    first = torch.cat([it.response.codes for it in items[:i0]], dim=1)
+    assert set(acts[:i0]) == {"partial"} and torch.equal(first.to(items[i0].response.codes.dtype), items[i0].response.codes)
+    i1 = acts.index("sample", i0 + 1)
+    second = torch.cat([it.response.codes for it in items[i0 + 1:i1]], dim=1)
+    assert torch.equal(second.to(items[i1].response.codes.dtype), items[i1].response.codes)
+    plain = []
+    while not rn.empty():
+        plain.append(rn.get_nowait().response.action)
+    assert plain == ["sample", "sample", "next"]
