@@ -145,6 +145,53 @@ def encode_batch(clips: Sequence[Clip], model) -> float:
     return sum(lens) / float(model.sample_rate)
 
 
+def decode_audio_bytes(data: bytes) -> tuple[torch.Tensor, int]:
+    """Mono float32 waveform [N] and sample rate of an encoded audio file held in memory (the server receives reference
+    audio as bytes): soundfile, then the stdlib PCM-wav reader."""
+    import io
+
+    try:
+        import soundfile as sf
+
+        x, sr = sf.read(io.BytesIO(data), dtype="float32", always_2d=True)
+        return torch.from_numpy(x).mean(dim=1), int(sr)
+    except Exception:
+        pass
+    with wave.open(io.BytesIO(data), "rb") as f:
+        sr, nch, width, n = f.getframerate(), f.getnchannels(), f.getsampwidth(), f.getnframes()
+        raw = f.readframes(n)
+    if width != 2:
+        raise ValueError(f"unsupported PCM width {width} in an in-memory wav")
+    x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+    return torch.from_numpy(x.reshape(-1, nch).mean(axis=1).copy()), int(sr)
+
+
+@torch.inference_mode()
+def batch_encode(model, audios_list: Sequence) -> list[torch.Tensor]:
+    """tools/server/model_utils.py:15-48: several reference audios (encoded bytes, or waveforms [1, N] at the codec's
+    sample rate) -> one padded `model.encode` call -> per item its codes [n_codebooks, frames_i] on the host, padding
+    frames cut off. (The reference runs this under fp16 autocast; the CUDA codec computes in bf16 / fp32 accumulate.)"""
+    sr = int(model.sample_rate)
+    audios = []
+    for a in audios_list:
+        if isinstance(a, (bytes, bytearray)):
+            wav, file_sr = decode_audio_bytes(bytes(a))
+            audios.append(resample(wav, file_sr, sr)[None])
+        else:
+            audios.append(torch.as_tensor(a, dtype=torch.float32).reshape(1, -1))
+    if not audios:
+        return []
+    device = model.device
+    lens = [int(x.shape[-1]) for x in audios]
+    padded = torch.zeros(len(audios), 1, max(lens), dtype=torch.float32)
+    for k, x in enumerate(audios):
+        padded[k, 0, : lens[k]] = x[0]
+    lengths = torch.tensor(lens, device=device, dtype=torch.long)
+    features, feature_lengths = model.encode(padded.to(device), lengths)
+    features, feature_lengths = features.cpu(), feature_lengths.cpu()
+    return [f[..., : int(n)] for f, n in zip(features, feature_lengths)]
+
+
 def encode_files(files: Sequence[Path], model, batch_size: int = 64, max_batch_seconds: float = 1800.0,
                  reader: Callable[[Path], tuple[torch.Tensor, int]] = read_audio, prefetch: int = 2,
                  progress: Optional[Callable[[int, float], None]] = None) -> tuple[int, float]:

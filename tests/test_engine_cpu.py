@@ -648,3 +648,19 @@ def test_slot_scheduler_worker_sends_partials_for_streaming_requests(monkeypatch
     while not rn.empty():
         plain.append(rn.get_nowait().response.action)
     assert plain == ["sample", "sample", "next"]
+
+
+def test_batch_encode_pads_once_and_cuts_each_item(tmp_path):
+    """bulk_encode.batch_encode (tools/server/model_utils.py:15-48): encoded bytes and waveforms mixed, ONE padded
+    encode call, per-item codes cut to that item's frames."""
+    from fish_speech_b200 import bulk_encode as BE
+
+    codec = _FakeCodec()
+    f = tmp_path / "a.wav"
+    _write_wav(f, 57, sr=100)
+    items = [f.read_bytes(), torch.zeros(1, 31), torch.zeros(1, 90)]
+    outs = BE.batch_encode(codec, items)
+    assert codec.batches == [(3, 90, [57, 31, 90])]
+    assert [tuple(o.shape) for o in outs] == [(3, 6), (3, 4), (3, 9)]
+    assert int(outs[0][1, 0]) == 1 + 570 and int(outs[2][2, -1]) == 2 + 900
+    assert BE.batch_encode(codec, []) == []
