@@ -664,3 +664,42 @@ def test_batch_encode_pads_once_and_cuts_each_item(tmp_path):
     assert [tuple(o.shape) for o in outs] == [(3, 6), (3, 4), (3, 9)]
     assert int(outs[0][1, 0]) == 1 + 570 and int(outs[2][2, -1]) == 2 + 900
     assert BE.batch_encode(codec, []) == []
+
+
+def test_reference_loader_caches_by_hash_and_by_id(tmp_path, monkeypatch):
+    """ReferenceLoader (reference_loader.py:62-160): one encode per distinct uploaded audio unless the request turns the
+    cache off; library ids are validated and read clip + .lab pairs; load_audio decodes bytes and paths to mono float32."""
+    from fish_speech_b200.inference_engine import reference_loader as RL
+
+    monkeypatch.setattr(RL, "LIBRARY", tmp_path / "references")
+    calls = []
+
+    class L(RL.ReferenceLoader):
+        def encode_reference(self, reference_audio, enable_reference_audio):
+            calls.append(len(reference_audio))
+            return torch.full((2, 3), len(reference_audio))
+
+    ld = L()
+    R = lambda a, t: type("Ref", (), dict(audio=a, text=t))()
+    refs = [R(b"aaaa", "one"), R(b"bb", "two"), R(b"aaaa", "one again")]
+    toks, texts = ld.load_by_hash(refs, "on")
+    assert calls == [4, 2] and texts == ["one", "two", "one"] and int(toks[2][0, 0]) == 4
+    ld.load_by_hash(refs[:1], "on")
+    assert calls == [4, 2]
+    ld.load_by_hash(refs[:1], "off")
+    assert calls == [4, 2, 4]
+    with pytest.raises(ValueError):
+        ld.load_by_id("../etc", "on")
+    d = tmp_path / "references" / "voice 1"
+    d.mkdir(parents=True)
+    _write_wav(d / "a.wav", 50, sr=100)
+    (d / "a.lab").write_text("hello", encoding="utf-8")
+    (d / "notes.txt").write_text("x")
+    toks, texts = ld.load_by_id("voice 1", "on")
+    assert texts == ["hello"] and len(toks) == 1 and ld.list_reference_ids() == ["voice 1"]
+    n = len(calls)
+    ld.load_by_id("voice 1", "on")
+    assert len(calls) == n
+    wav = ld.load_audio((d / "a.wav").read_bytes(), 100)
+    assert wav.dtype == np.float32 and wav.shape == (50,)
+    assert np.array_equal(ld.load_audio(str(d / "a.wav"), 100), wav)
