@@ -703,3 +703,19 @@ def test_reference_loader_caches_by_hash_and_by_id(tmp_path, monkeypatch):
     wav = ld.load_audio((d / "a.wav").read_bytes(), 100)
     assert wav.dtype == np.float32 and wav.shape == (50,)
     assert np.array_equal(ld.load_audio(str(d / "a.wav"), 100), wav)
+
+
+def test_wav_chunk_header_is_the_header_of_an_empty_pcm_wav():
+    import io
+    import wave
+
+    from fish_speech_b200.inference_engine.utils import pcm16, wav_chunk_header
+
+    for sr, bits, ch in ((44100, 16, 1), (16000, 16, 2), (48000, 32, 1)):
+        buf = io.BytesIO()
+        with wave.open(buf, "wb") as f:
+            f.setnchannels(ch)
+            f.setsampwidth(bits // 8)
+            f.setframerate(sr)
+        assert wav_chunk_header(sr, bits, ch) == buf.getvalue()
+    assert pcm16(np.array([0.0, 1.0, -1.0, 2.0, 0.5])) == np.array([0, 32767, -32767, 32767, 16383], dtype="<i2").tobytes()
